@@ -1,0 +1,564 @@
+#include "engine.h"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+namespace ju {
+
+namespace {
+
+int pad64(int c) { return (c + 63) / 64 * 64; }
+int pad16(int c) { return (c + 15) / 16 * 16; }
+
+int envInt(const char *name, int fallback) {
+	const char *v = std::getenv(name);
+	return v ? std::atoi(v) : fallback;
+}
+
+}  // namespace
+
+Engine::Engine(const ModelFile &model, int device, int batch)
+    : m_Spec(model.spec()), m_Device(device), m_Batch(batch) {
+	if (batch < 1 || batch > 64) throw std::invalid_argument("batch must be in [1, 64]");
+	int count = 0;
+	JU_CUDA(cudaGetDeviceCount(&count));
+	if (device < 0 || device >= count) throw std::invalid_argument("invalid CUDA device index");
+	DeviceGuard guard(device);
+	cudaDeviceProp prop{};
+	JU_CUDA(cudaGetDeviceProperties(&prop, device));
+	if (prop.major != 10) {
+		JU_LOG_WARN << "device " << device << " is sm_" << prop.major << prop.minor
+		            << "; kernels are built for sm_100a only";
+	}
+	m_ConvImpl = envInt("JU_CONV_IMPL", 0);
+	m_UseGraph = envInt("JU_NO_GRAPH", 0) == 0;
+	JU_CUDA(cudaStreamCreateWithFlags(&m_Stream, cudaStreamNonBlocking));
+	try {
+		buildLayers(model);
+		allocate();
+		buildPlan(0);
+		buildPlan(1);
+		if (m_UseGraph) {
+			capture(0);
+			capture(1);
+		}
+		JU_CUDA(cudaStreamSynchronize(m_Stream));
+	} catch (...) {
+		for (auto &g : m_GraphExec)
+			if (g) cudaGraphExecDestroy(g);
+		cudaStreamDestroy(m_Stream);
+		throw;
+	}
+	JU_LOG_INFO << "engine ready: " << m_Spec.frameW << "x" << m_Spec.frameH << " -> "
+	            << 4 * m_Spec.frameW << "x" << 4 * m_Spec.frameH << ", batch " << m_Batch << ", "
+	            << m_Plans[0].size() << " kernels/frame, conv impl " << m_ConvImpl;
+}
+
+Engine::~Engine() {
+	cudaSetDevice(m_Device);
+	cudaStreamSynchronize(m_Stream);
+	for (auto &g : m_GraphExec)
+		if (g) cudaGraphExecDestroy(g);
+	cudaStreamDestroy(m_Stream);
+}
+
+// ---------------------------------------------------------------------------
+// layers
+// ---------------------------------------------------------------------------
+
+ConvLayer *Engine::addConv(const std::string &name, const FoldedConv &f, int act, float slope,
+    bool shuffle2) {
+	auto layer = std::make_unique<ConvLayer>();
+	layer->name = name;
+	layer->ksize = f.ksize;
+	layer->cinReal = f.cin;
+	layer->cin = pad16(f.cin);
+	layer->cout = f.cout;
+	layer->shuffle2 = shuffle2;
+	layer->act = act;
+	layer->slope = slope;
+	std::vector<__half> packed(conv_simt_weight_bytes(f.ksize, layer->cin, f.cout) / sizeof(__half));
+	conv_simt_pack_weights(f.kernel.data(), f.scale.data(), f.ksize, f.cin, layer->cin, f.cout,
+	    packed.data());
+	layer->wSimt = DeviceBuffer(packed.size() * sizeof(__half));
+	layer->wSimt.upload(packed.data(), packed.size() * sizeof(__half));
+	layer->bias = DeviceBuffer(f.bias.size() * sizeof(float));
+	layer->bias.upload(f.bias.data(), f.bias.size() * sizeof(float));
+	ConvLayer *raw = layer.get();
+	m_LayerByName[name] = raw;
+	m_Layers.push_back(std::move(layer));
+	return raw;
+}
+
+void Engine::buildLayers(const ModelFile &model) {
+	const ModelSpec &s = m_Spec;
+	const int actF = s.actFlow == 0 ? ACT_RELU : ACT_LRELU;
+	const int actG = s.actGen == 0 ? ACT_RELU : ACT_LRELU;
+	if (3 * s.flowInputs > 64) throw ModelException("too many flow inputs");
+	if (s.flowArch == 0) {
+		int n = static_cast<int>(s.flowFilters.size()) / 2;
+		for (int i = 0; i < 2 * n; ++i) {
+			std::string p = "flow/block_" + std::to_string(i + 1);
+			addConv(p + "/conv_1", model.foldConv(p + "/conv_1", p + "/bn_1"), actF, s.slopeFlow, false);
+			addConv(p + "/conv_2", model.foldConv(p + "/conv_2", p + "/bn_2"), actF, s.slopeFlow, false);
+		}
+		if (s.flowFilters.size() % 2) {
+			addConv("flow/conv_1", model.foldConv("flow/conv_1", "flow/bn_1"), actF, s.slopeFlow, false);
+		}
+	} else {
+		addConv("flow/conv_1", model.foldConv("flow/conv_1", "flow/bn_1"), actF, s.slopeFlow, false);
+		for (int i = 0; i < s.flowFilters[1]; ++i) {
+			std::string p = "flow/block_" + std::to_string(i + 1);
+			addConv(p + "/conv_1", model.foldConv(p + "/conv_1", p + "/bn_1"), actF, s.slopeFlow, false);
+			addConv(p + "/conv_2", model.foldConv(p + "/conv_2", p + "/bn_2"), actF, s.slopeFlow, false);
+		}
+	}
+	ConvLayer *head = addConv("flow/conv_2", model.foldConv("flow/conv_2", ""), ACT_NONE, 0.f, false);
+	if (head->cout != 32) throw ModelException("flow head must have 32 channels");
+
+	addConv("generator/conv_1", model.foldConv("generator/conv_1", "generator/bn_1"), actG, s.slopeGen, false);
+	for (int i = 0; i < s.genBlocks; ++i) {
+		std::string p = "generator/block_" + std::to_string(i + 1);
+		addConv(p + "/conv_1", model.foldConv(p + "/conv_1", p + "/bn_1"), actG, s.slopeGen, false);
+		addConv(p + "/conv_2", model.foldConv(p + "/conv_2", p + "/bn_2"), actG, s.slopeGen, false);
+	}
+	ConvLayer *ct1 = addConv("generator/conv_trans_1",
+	    model.foldConvTranspose("generator/conv_trans_1", "generator/bn_2"), actG, s.slopeGen, true);
+	if (ct1->cout != 128) throw ModelException("conv_trans_1 must have 32 filters");
+
+	// conv_trans_2 (2,2,3,32) + bias -> [q][o][c] fp32 for the fused final kernel;
+	// weights are rounded to fp16 precision (engine storage contract)
+	const HostTensor &k2 = model.tensor("generator/conv_trans_2/kernel");
+	if (k2.dims != std::vector<int>{2, 2, 3, 32}) throw ModelException("conv_trans_2 must be (2,2,3,32)");
+	std::vector<float> w2(k2.data.size());
+	for (std::size_t i = 0; i < w2.size(); ++i) w2[i] = __half2float(__float2half_rn(k2.data[i]));
+	m_W2 = DeviceBuffer(w2.size() * sizeof(float));
+	m_W2.upload(w2.data(), w2.size() * sizeof(float));
+	const auto &b2 = model.tensor("generator/conv_trans_2/bias").data;
+	m_B2 = DeviceBuffer(3 * sizeof(float));
+	m_B2.upload(b2.data(), 3 * sizeof(float));
+}
+
+// ---------------------------------------------------------------------------
+// buffers
+// ---------------------------------------------------------------------------
+
+void Engine::registerTensor(const std::string &name, void *p0, void *p1, int dtype,
+    std::vector<std::uint64_t> dims, std::size_t bytes, bool writable) {
+	NamedTensor t;
+	t.ptr[0] = p0;
+	t.ptr[1] = p1;
+	t.pingPong = p1 != nullptr;
+	t.dtype = dtype;
+	t.dims = std::move(dims);
+	t.bytes = bytes;
+	t.writable = writable;
+	m_Tensors[name] = std::move(t);
+}
+
+void Engine::allocate() {
+	const ModelSpec &s = m_Spec;
+	const std::uint64_t B = m_Batch, H = s.frameH, W = s.frameW, PH = s.padH, PW = s.padW;
+	m_IoHost = PinnedBuffer(sizeof(FrameIO) * B);
+	m_IoDev = DeviceBuffer(sizeof(FrameIO) * B);
+	m_InStage = DeviceBuffer(B * H * W * 4);
+	m_OutStage = DeviceBuffer(B * 16 * H * W * 4);
+	m_FlowCStride = 64;
+	for (int p = 0; p < 2; ++p) {
+		m_FlowIn[p] = DeviceBuffer(B * PH * PW * m_FlowCStride * sizeof(__half));
+		m_PreGen[p] = DeviceBuffer(B * 16 * H * W * 4 * sizeof(__half));
+	}
+	m_FlowHead = DeviceBuffer(B * PH * PW * 32 * sizeof(float));
+	const int gstride = pad64(std::max(m_Spec.genFilters, 51));
+	m_GenIn = DeviceBuffer(B * H * W * 64 * sizeof(__half));
+	for (auto &t : m_Trunk) t = DeviceBuffer(B * H * W * gstride * sizeof(__half));
+	m_Mid = DeviceBuffer(B * 4 * H * W * 32 * sizeof(__half));
+
+	registerTensor("flow_in", m_FlowIn[0].get(), m_FlowIn[1].get(), 1,
+	    {B, PH, PW, static_cast<std::uint64_t>(m_FlowCStride)}, m_FlowIn[0].bytes(), true);
+	registerTensor("pre_gen", m_PreGen[0].get(), m_PreGen[1].get(), 1, {B, 4 * H, 4 * W, 4},
+	    m_PreGen[0].bytes(), true);
+	registerTensor("flow_head", m_FlowHead.get(), nullptr, 0, {B, PH, PW, 32}, m_FlowHead.bytes(), false);
+	registerTensor("gen_in", m_GenIn.get(), nullptr, 1, {B, H, W, 64}, m_GenIn.bytes(), false);
+	registerTensor("mid", m_Mid.get(), nullptr, 1, {B, 2 * H, 2 * W, 32}, m_Mid.bytes(), false);
+
+	// default frame table: staging buffers (used until the first bindImages)
+	FrameIO *io = m_IoHost.as<FrameIO>();
+	for (std::uint64_t b = 0; b < B; ++b) {
+		io[b].in = m_InStage.as<std::uint8_t>() + b * H * W * 4;
+		io[b].in_stride = static_cast<long long>(W * 4);
+		io[b].out = m_OutStage.as<std::uint8_t>() + b * 16 * H * W * 4;
+		io[b].out_stride = static_cast<long long>(4 * W * 4);
+	}
+	JU_CUDA(cudaMemcpy(m_IoDev.get(), io, sizeof(FrameIO) * B, cudaMemcpyHostToDevice));
+}
+
+DeviceBuffer &Engine::newActivation(std::size_t bytes) {
+	m_Activations.push_back(std::make_unique<DeviceBuffer>(bytes));
+	return *m_Activations.back();
+}
+
+// ---------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------
+
+Op Engine::convOp(ConvLayer *L, const __half *in, int cinStride, const __half *residual, void *out,
+    int coutStride, int h, int w, bool outF32) {
+	ConvArgs a{};
+	a.in = in;
+	a.weights = L->wSimt.get();
+	a.bias = L->bias.as<float>();
+	a.residual = residual;
+	a.out = out;
+	a.batch = m_Batch;
+	a.h = h;
+	a.w = w;
+	a.cin_stride = cinStride;
+	a.cin = L->cin;
+	a.cout = L->cout;
+	a.cout_stride = coutStride;
+	a.ksize = L->ksize;
+	a.act = L->act;
+	a.slope = L->slope;
+	a.out_f32 = outF32 ? 1 : 0;
+	a.shuffle2 = L->shuffle2 ? 1 : 0;
+	if (a.cin > cinStride) throw ModelException("channel stride too small for " + L->name);
+	Op op;
+	op.name = L->name;
+	op.tensorBound = true;
+	op.flops = 2.0 * m_Batch * h * w * L->ksize * L->ksize * L->cinReal * L->cout;
+	op.bytes = static_cast<double>(m_Batch) * h * w *
+	           (L->cinReal * 2.0 + L->cout * (outF32 ? 4.0 : 2.0) + (residual ? L->cout * 2.0 : 0.0));
+	op.run = [a](cudaStream_t s) { return launch_conv_simt(a, s); };
+	return op;
+}
+
+void Engine::buildPlan(int parity) {
+	const ModelSpec &s = m_Spec;
+	const int B = m_Batch, H = s.frameH, W = s.frameW, PH = s.padH, PW = s.padW;
+	std::vector<Op> &plan = m_Plans[parity];
+	plan.clear();
+	std::size_t actCursor = 0;
+	auto activation = [&](std::size_t bytes) -> __half * {
+		if (parity == 0) return newActivation(bytes).as<__half>();
+		DeviceBuffer &buf = *m_Activations.at(actCursor++);
+		if (buf.bytes() != bytes) throw std::logic_error("activation plan mismatch");
+		return buf.as<__half>();
+	};
+	auto layer = [&](const std::string &name) -> ConvLayer * { return m_LayerByName.at(name); };
+	const FrameIO *io = m_IoDev.as<FrameIO>();
+
+	// parity p reads state set p and writes set p^1 (tensorrt_backend.cc:247-256)
+	const __half *flowPrev = m_FlowIn[parity].as<__half>();
+	__half *flowNext = m_FlowIn[parity ^ 1].as<__half>();
+	const __half *preGenPrev = m_PreGen[parity].as<__half>();
+	__half *preGenNext = m_PreGen[parity ^ 1].as<__half>();
+
+	{
+		Op op;
+		op.name = "preprocess";
+		const int k = s.flowInputs, cs = m_FlowCStride;
+		op.bytes = static_cast<double>(B) * (H * W * 4.0 + PH * PW * (3.0 * (k - 1) * 2 + 3.0 * k * 2));
+		op.run = [=](cudaStream_t st) {
+			return launch_preprocess(io, flowPrev, flowNext, B, H, W, PH, PW, k, cs, st);
+		};
+		plan.push_back(std::move(op));
+	}
+
+	// ---- flow net ------------------------------------------------------
+	const __half *x = flowNext;
+	int xs = m_FlowCStride, h = PH, w = PW;
+	auto conv = [&](const std::string &name, const __half *residual = nullptr) {
+		ConvLayer *L = layer(name);
+		int os = pad64(L->cout);
+		__half *out = activation(static_cast<std::size_t>(B) * h * w * os * sizeof(__half));
+		plan.push_back(convOp(L, x, xs, residual, out, os, h, w, false));
+		x = out;
+		xs = os;
+	};
+	if (s.flowArch == 0) {
+		int n = static_cast<int>(s.flowFilters.size()) / 2;
+		for (int i = 0; i < 2 * n; ++i) {
+			std::string p = "flow/block_" + std::to_string(i + 1);
+			conv(p + "/conv_1");
+			conv(p + "/conv_2");
+			const __half *src = x;
+			const int c = xs, hh = h, ww = w;
+			Op op;
+			if (i < n) {
+				__half *out = activation(static_cast<std::size_t>(B) * (h / 2) * (w / 2) * c * sizeof(__half));
+				op.name = p + "/max_pool";
+				op.bytes = static_cast<double>(B) * hh * ww * s.flowFilters[i] * 2.0 * 1.25;
+				op.run = [=](cudaStream_t st) { return launch_maxpool2(src, out, B, hh, ww, c, st); };
+				h /= 2;
+				w /= 2;
+				x = out;
+			} else {
+				__half *out = activation(static_cast<std::size_t>(B) * (h * 2) * (w * 2) * c * sizeof(__half));
+				op.name = p + "/upscale";
+				op.bytes = static_cast<double>(B) * hh * ww * s.flowFilters[i] * 2.0 * 5.0;
+				op.run = [=](cudaStream_t st) { return launch_upscale2(src, out, B, hh, ww, c, st); };
+				h *= 2;
+				w *= 2;
+				x = out;
+			}
+			plan.push_back(std::move(op));
+		}
+		if (s.flowFilters.size() % 2) conv("flow/conv_1");
+	} else {
+		conv("flow/conv_1");
+		for (int i = 0; i < s.flowFilters[1]; ++i) {
+			std::string p = "flow/block_" + std::to_string(i + 1);
+			const __half *shortcut = x;
+			conv(p + "/conv_1");
+			conv(p + "/conv_2", shortcut);
+		}
+	}
+	if (h != PH || w != PW) throw ModelException("flow net does not return to input resolution");
+	plan.push_back(convOp(layer("flow/conv_2"), x, xs, nullptr, m_FlowHead.get(), 32, PH, PW, true));
+
+	// ---- warp + space-to-depth + concat --------------------------------
+	{
+		Op op;
+		op.name = "warp_s2d";
+		__half *genIn = m_GenIn.as<__half>();
+		const float *head = m_FlowHead.as<float>();
+		// read state (3ch fp16) + read flow (2 x fp32 here) + write warped (3ch fp16), SURVEY 8(d)
+		op.bytes = static_cast<double>(B) * 16.0 * H * W * (3 * 2 + 2 * 4 + 3 * 2);
+		op.run = [=](cudaStream_t st) {
+			return launch_warp_s2d(preGenPrev, head, io, genIn, nullptr, nullptr, B, H, W, PH, PW, 64, st);
+		};
+		plan.push_back(std::move(op));
+	}
+
+	// ---- generator -----------------------------------------------------
+	const int gs = pad64(std::max(s.genFilters, 51));
+	__half *t0 = m_Trunk[0].as<__half>(), *t1 = m_Trunk[1].as<__half>(), *t2 = m_Trunk[2].as<__half>();
+	plan.push_back(convOp(layer("generator/conv_1"), m_GenIn.as<__half>(), 64, nullptr, t0, gs, H, W, false));
+	__half *cur = t0, *tmp = t1, *nxt = t2;
+	for (int i = 0; i < s.genBlocks; ++i) {
+		std::string p = "generator/block_" + std::to_string(i + 1);
+		plan.push_back(convOp(layer(p + "/conv_1"), cur, gs, nullptr, tmp, gs, H, W, false));
+		plan.push_back(convOp(layer(p + "/conv_2"), tmp, gs, cur, nxt, gs, H, W, false));
+		std::swap(cur, nxt);
+	}
+	if (parity == 0) {
+		registerTensor("trunk", cur, nullptr, 1,
+		    {static_cast<std::uint64_t>(B), static_cast<std::uint64_t>(H), static_cast<std::uint64_t>(W),
+		        static_cast<std::uint64_t>(gs)},
+		    m_Trunk[0].bytes(), false);
+	}
+	plan.push_back(convOp(layer("generator/conv_trans_1"), cur, gs, nullptr, m_Mid.get(), 32, H, W, false));
+	{
+		Op op;
+		op.name = "final";
+		const __half *mid = m_Mid.as<__half>();
+		const float *w2 = m_W2.as<float>(), *b2 = m_B2.as<float>();
+		// read mid (32ch fp16 @2Hx2W) + LR input + write BGRX u8 + fp16 state (3ch), SURVEY 8(d)
+		op.bytes = static_cast<double>(B) * (4.0 * H * W * 32 * 2 + H * W * 4.0 + 16.0 * H * W * (4 + 3 * 2));
+		op.flops = 2.0 * B * 4.0 * H * W * 32 * 12;
+		op.run = [=](cudaStream_t st) {
+			return launch_final(mid, w2, b2, io, preGenNext, nullptr, nullptr, B, H, W, st);
+		};
+		plan.push_back(std::move(op));
+	}
+}
+
+void Engine::capture(int parity) {
+	cudaGraph_t graph = nullptr;
+	JU_CUDA(cudaStreamBeginCapture(m_Stream, cudaStreamCaptureModeThreadLocal));
+	cudaError_t err = cudaSuccess;
+	for (const Op &op : m_Plans[parity]) {
+		err = op.run(m_Stream);
+		if (err != cudaSuccess) break;
+	}
+	cudaError_t endErr = cudaStreamEndCapture(m_Stream, &graph);
+	checkCuda(err, "kernel launch during graph capture");
+	checkCuda(endErr, "cudaStreamEndCapture");
+	cudaError_t instErr = cudaGraphInstantiate(&m_GraphExec[parity], graph, 0);
+	cudaGraphDestroy(graph);
+	checkCuda(instErr, "cudaGraphInstantiate");
+}
+
+// ---------------------------------------------------------------------------
+// per-frame
+// ---------------------------------------------------------------------------
+
+void Engine::bindImages(int n, const ju_image *inputs, const ju_image *outputs) {
+	const std::size_t H = m_Spec.frameH, W = m_Spec.frameW;
+	const std::size_t inRow = W * 4, outRow = 4 * W * 4;
+	FrameIO *io = m_IoHost.as<FrameIO>();
+	m_LastOutputs.assign(outputs, outputs + n);
+	m_OutputNeedsCopy.assign(n, false);
+	for (int s = 0; s < m_Batch; ++s) {
+		std::uint8_t *inStage = m_InStage.as<std::uint8_t>() + s * H * inRow;
+		std::uint8_t *outStage = m_OutStage.as<std::uint8_t>() + s * 4 * H * outRow;
+		FrameIO &f = io[s];
+		if (s >= n) {
+			f.in = inStage;
+			f.in_stride = static_cast<long long>(inRow);
+			f.out = outStage;
+			f.out_stride = static_cast<long long>(outRow);
+			continue;
+		}
+		const ju_image &in = inputs[s];
+		const ju_image &out = outputs[s];
+		if (in.width != W || in.height != H || out.width != 4 * W || out.height != 4 * H) {
+			throw std::invalid_argument("image size does not match the model (input " +
+			                            std::to_string(W) + "x" + std::to_string(H) + ", output " +
+			                            std::to_string(4 * W) + "x" + std::to_string(4 * H) + ")");
+		}
+		if (!in.ptr || !out.ptr) throw std::invalid_argument("null image pointer");
+		auto absStride = [](std::int64_t v) { return static_cast<std::size_t>(v < 0 ? -v : v); };
+		if (in.location == JU_LOC_CPU) {
+			if (absStride(in.stride) < inRow) throw std::invalid_argument("input stride smaller than a row");
+			const auto *p = static_cast<const std::uint8_t *>(in.ptr);
+			if (in.stride >= 0) {
+				JU_CUDA(cudaMemcpy2DAsync(inStage, inRow, p, in.stride, inRow, H, cudaMemcpyHostToDevice, m_Stream));
+				f.in = inStage;
+				f.in_stride = static_cast<long long>(inRow);
+			} else {
+				// bottom-up: ptr addresses the last memory row (avisynth main.cc:125-142)
+				const std::uint8_t *lowest = p + static_cast<std::int64_t>(H - 1) * in.stride;
+				JU_CUDA(cudaMemcpy2DAsync(inStage, inRow, lowest, -in.stride, inRow, H, cudaMemcpyHostToDevice, m_Stream));
+				f.in = inStage + (H - 1) * inRow;
+				f.in_stride = -static_cast<long long>(inRow);
+			}
+		} else if (in.location == JU_LOC_CUDA) {
+			f.in = static_cast<const std::uint8_t *>(in.ptr);
+			f.in_stride = in.stride;
+		} else {
+			throw std::invalid_argument("GRAPHICS_RESOURCE images need a GL/D3D11 build (headless B200 build)");
+		}
+		if (out.location == JU_LOC_CPU) {
+			if (absStride(out.stride) < outRow) throw std::invalid_argument("output stride smaller than a row");
+			m_OutputNeedsCopy[s] = true;
+			if (out.stride >= 0) {
+				f.out = outStage;
+				f.out_stride = static_cast<long long>(outRow);
+			} else {
+				f.out = outStage + (4 * H - 1) * outRow;
+				f.out_stride = -static_cast<long long>(outRow);
+			}
+		} else if (out.location == JU_LOC_CUDA) {
+			f.out = static_cast<std::uint8_t *>(out.ptr);
+			f.out_stride = out.stride;
+		} else {
+			throw std::invalid_argument("GRAPHICS_RESOURCE images need a GL/D3D11 build (headless B200 build)");
+		}
+	}
+	JU_CUDA(cudaMemcpyAsync(m_IoDev.get(), io, sizeof(FrameIO) * m_Batch, cudaMemcpyHostToDevice, m_Stream));
+}
+
+void Engine::process(int n, const ju_image *inputs, const ju_image *outputs) {
+	if (n < 1 || n > m_Batch) throw std::invalid_argument("image count must be in [1, batch]");
+	DeviceGuard guard(m_Device);
+	const std::size_t H = m_Spec.frameH, W = m_Spec.frameW, outRow = 4 * W * 4;
+	try {
+		bindImages(n, inputs, outputs);
+		if (m_UseGraph) {
+			JU_CUDA(cudaGraphLaunch(m_GraphExec[m_Parity], m_Stream));
+		} else {
+			for (const Op &op : m_Plans[m_Parity]) checkCuda(op.run(m_Stream), op.name.c_str());
+		}
+		for (int s = 0; s < n; ++s) {
+			if (!m_OutputNeedsCopy[s]) continue;
+			const ju_image &out = outputs[s];
+			const std::uint8_t *stage = m_OutStage.as<std::uint8_t>() + s * 4 * H * outRow;
+			auto *p = static_cast<std::uint8_t *>(out.ptr);
+			if (out.stride >= 0) {
+				JU_CUDA(cudaMemcpy2DAsync(p, out.stride, stage, outRow, outRow, 4 * H, cudaMemcpyDeviceToHost, m_Stream));
+			} else {
+				std::uint8_t *lowest = p + static_cast<std::int64_t>(4 * H - 1) * out.stride;
+				JU_CUDA(cudaMemcpy2DAsync(lowest, -out.stride, stage, outRow, outRow, 4 * H, cudaMemcpyDeviceToHost, m_Stream));
+			}
+		}
+		JU_CUDA(cudaStreamSynchronize(m_Stream));
+	} catch (...) {
+		// a failed frame leaves the ping-pong index unchanged (the reference
+		// flips only after the synchronize, tensorrt_backend.cc:276-277)
+		cudaStreamSynchronize(m_Stream);
+		throw;
+	}
+	m_Parity ^= 1;
+}
+
+void Engine::resetState() {
+	DeviceGuard guard(m_Device);
+	JU_CUDA(cudaStreamSynchronize(m_Stream));
+	for (int p = 0; p < 2; ++p) {
+		JU_CUDA(cudaMemset(m_FlowIn[p].get(), 0, m_FlowIn[p].bytes()));
+		JU_CUDA(cudaMemset(m_PreGen[p].get(), 0, m_PreGen[p].bytes()));
+	}
+	m_Parity = 0;
+}
+
+void Engine::readTensor(const std::string &name, void *dst, std::uint64_t capacity, ju_tensor_desc *desc) {
+	auto it = m_Tensors.find(name);
+	if (it == m_Tensors.end()) throw std::invalid_argument("unknown tensor " + name);
+	const NamedTensor &t = it->second;
+	if (desc) {
+		desc->dtype = static_cast<std::uint32_t>(t.dtype);
+		desc->ndim = static_cast<std::uint32_t>(t.dims.size());
+		for (std::size_t i = 0; i < 4; ++i) desc->dims[i] = i < t.dims.size() ? t.dims[i] : 1;
+		desc->bytes = t.bytes;
+	}
+	if (!dst) return;
+	if (capacity < t.bytes) throw std::invalid_argument("destination too small for " + name);
+	DeviceGuard guard(m_Device);
+	// ping-pong tensors: the set the NEXT frame will read (= newest state)
+	void *src = t.pingPong ? t.ptr[m_Parity] : t.ptr[0];
+	JU_CUDA(cudaStreamSynchronize(m_Stream));
+	JU_CUDA(cudaMemcpy(dst, src, t.bytes, cudaMemcpyDeviceToHost));
+}
+
+void Engine::writeState(const std::string &name, const void *srcHost, std::uint64_t bytes) {
+	auto it = m_Tensors.find(name);
+	if (it == m_Tensors.end() || !it->second.writable) throw std::invalid_argument("not a state tensor: " + name);
+	const NamedTensor &t = it->second;
+	if (bytes != t.bytes) throw std::invalid_argument("size mismatch for " + name);
+	DeviceGuard guard(m_Device);
+	JU_CUDA(cudaStreamSynchronize(m_Stream));
+	JU_CUDA(cudaMemcpy(t.ptr[m_Parity], srcHost, bytes, cudaMemcpyHostToDevice));
+}
+
+std::vector<ju_op_time> Engine::profileOps(int iters) {
+	if (iters < 1) iters = 1;
+	DeviceGuard guard(m_Device);
+	JU_CUDA(cudaStreamSynchronize(m_Stream));
+	const std::vector<Op> &plan = m_Plans[m_Parity];
+	std::vector<cudaEvent_t> ev(plan.size() + 1);
+	for (auto &e : ev) JU_CUDA(cudaEventCreate(&e));
+	std::vector<double> total(plan.size(), 0.0);
+	// state is advanced in place on parity m_Parity without flipping: the
+	// timings are data-independent, and the caller resets state afterwards
+	for (int it = -2; it < iters; ++it) {
+		JU_CUDA(cudaEventRecord(ev[0], m_Stream));
+		for (std::size_t i = 0; i < plan.size(); ++i) {
+			checkCuda(plan[i].run(m_Stream), plan[i].name.c_str());
+			JU_CUDA(cudaEventRecord(ev[i + 1], m_Stream));
+		}
+		JU_CUDA(cudaStreamSynchronize(m_Stream));
+		if (it < 0) continue;  // warm-up
+		for (std::size_t i = 0; i < plan.size(); ++i) {
+			float ms = 0.f;
+			JU_CUDA(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+			total[i] += ms * 1000.0;
+		}
+	}
+	for (auto &e : ev) cudaEventDestroy(e);
+	std::vector<ju_op_time> result(plan.size());
+	for (std::size_t i = 0; i < plan.size(); ++i) {
+		ju_op_time &o = result[i];
+		std::memset(&o, 0, sizeof(o));
+		std::strncpy(o.name, plan[i].name.c_str(), sizeof(o.name) - 1);
+		o.usec = total[i] / iters;
+		o.flops = plan[i].flops;
+		o.bytes = plan[i].bytes;
+		o.tensor_bound = plan[i].tensorBound ? 1 : 0;
+	}
+	return result;
+}
+
+}  // namespace ju

@@ -1,0 +1,115 @@
+// The sm_100a engine behind Runtime::processImage.
+//
+// Takes over every responsibility of the reference's TensorRTBackend
+// (core/src/tensorrt_backend.cc:117-278): owning the device buffers, the
+// double-buffered recurrent state (m_InterBuffers, 213-218), one CUDA stream,
+// one captured CUDA graph per ping-pong parity (257-263), and the per-frame
+// sequence convert-in -> graph launch -> convert-out -> synchronize -> flip
+// (270-278).  The graph's nodes are this repo's hand-written kernels instead
+// of TensorRT tactics.  Extension over the reference: `batch` independent
+// streams advance in lockstep through one graph (batch folded into GEMM M).
+#pragma once
+
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../kernels/kernels.h"
+#include "common.h"
+#include "joshupscale_c.h"
+#include "model.h"
+
+namespace ju {
+
+struct ConvLayer {
+	std::string name;
+	int ksize = 3;
+	int cinReal = 0;  // channels in the Keras kernel
+	int cin = 0;      // reduced-over channels (padded to 16)
+	int cout = 0;
+	bool shuffle2 = false;
+	int act = ACT_NONE;
+	float slope = 0.f;
+	DeviceBuffer wSimt;
+	DeviceBuffer wTc;
+	DeviceBuffer bias;
+};
+
+struct Op {
+	std::string name;
+	std::function<cudaError_t(cudaStream_t)> run;
+	double flops = 0;  // algorithmic (true channel counts)
+	double bytes = 0;  // algorithmic bytes moved
+	bool tensorBound = false;
+};
+
+struct NamedTensor {
+	void *ptr[2] = {nullptr, nullptr};  // indexed by parity when `pingPong`
+	bool pingPong = false;
+	int dtype = 1;  // 0 f32, 1 f16, 2 u8
+	std::vector<std::uint64_t> dims;
+	std::size_t bytes = 0;
+	bool writable = false;
+};
+
+class Engine {
+public:
+	Engine(const ModelFile &model, int device, int batch);
+	~Engine();
+	Engine(const Engine &) = delete;
+	Engine &operator=(const Engine &) = delete;
+
+	const ModelSpec &spec() const { return m_Spec; }
+	int batch() const { return m_Batch; }
+	int device() const { return m_Device; }
+	int convImpl() const { return m_ConvImpl; }
+	std::size_t kernelsPerFrame() const { return m_Plans[0].size(); }
+
+	// n <= batch images; streams beyond n are advanced on their last input.
+	void process(int n, const ju_image *inputs, const ju_image *outputs);
+	void resetState();
+	void readTensor(const std::string &name, void *dst, std::uint64_t capacity, ju_tensor_desc *desc);
+	void writeState(const std::string &name, const void *src, std::uint64_t bytes);
+	std::vector<ju_op_time> profileOps(int iters);
+
+private:
+	void buildLayers(const ModelFile &model);
+	void allocate();
+	void buildPlan(int parity);
+	void capture(int parity);
+	ConvLayer *addConv(const std::string &name, const FoldedConv &f, int act, float slope, bool shuffle2);
+	Op convOp(ConvLayer *layer, const __half *in, int cinStride, const __half *residual, void *out,
+	    int coutStride, int h, int w, bool outF32);
+	DeviceBuffer &newActivation(std::size_t bytes);
+	void registerTensor(const std::string &name, void *p0, void *p1, int dtype,
+	    std::vector<std::uint64_t> dims, std::size_t bytes, bool writable);
+	void bindImages(int n, const ju_image *inputs, const ju_image *outputs);
+
+	ModelSpec m_Spec;
+	int m_Device = 0;
+	int m_Batch = 1;
+	int m_ConvImpl = 0;
+	bool m_UseGraph = true;
+	int m_Parity = 0;
+	cudaStream_t m_Stream = nullptr;
+	cudaGraphExec_t m_GraphExec[2] = {nullptr, nullptr};
+
+	PinnedBuffer m_IoHost;
+	DeviceBuffer m_IoDev;
+	DeviceBuffer m_InStage, m_OutStage;
+	std::vector<ju_image> m_LastOutputs;
+	std::vector<bool> m_OutputNeedsCopy;
+
+	DeviceBuffer m_FlowIn[2], m_PreGen[2];
+	DeviceBuffer m_FlowHead, m_GenIn, m_Trunk[3], m_Mid, m_W2, m_B2;
+	std::vector<std::unique_ptr<DeviceBuffer>> m_Activations;
+	std::vector<std::unique_ptr<ConvLayer>> m_Layers;
+	std::map<std::string, ConvLayer *> m_LayerByName;
+	std::vector<Op> m_Plans[2];
+	std::map<std::string, NamedTensor> m_Tensors;
+	int m_FlowCStride = 64;
+};
+
+}  // namespace ju

@@ -1,0 +1,64 @@
+// Internal launch interface of the sm_100a kernels.  Host code (engine.cc)
+// and the C-ABI (api.cc) call these; each returns the CUDA launch status.
+#pragma once
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace ju {
+
+// Per-stream frame addresses, read by the pixel-I/O kernels from DEVICE memory
+// so that a captured CUDA graph can be replayed on new images: the host
+// rewrites this small table before each launch instead of re-instantiating.
+// Strides are signed byte strides (bottom-up images have negative strides,
+// avisynth_plugin/src/main.cc:125-142).
+struct FrameIO {
+	const uint8_t *in;
+	long long in_stride;
+	uint8_t *out;
+	long long out_stride;
+};
+
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2 };
+
+struct ConvArgs {
+	const __half *in;        // [batch, h, w, cin_stride]
+	const void *weights;     // packed for the chosen impl
+	const float *bias;       // [cout] or nullptr
+	const __half *residual;  // [batch, h, w, cout_stride] or nullptr
+	void *out;               // fp16 or fp32; [batch, h, w, cout_stride] (shuffle2: [batch, 2h, 2w, cout_stride])
+	int batch, h, w;
+	int cin_stride;          // channel stride of `in` (elements)
+	int cin;                 // channels reduced over (multiple of 16, <= cin_stride)
+	int cout;                // output channels computed (shuffle2: 4 * per-pixel channels)
+	int cout_stride;         // channel stride of `out` / `residual`
+	int ksize;               // 1 or 3
+	int act;
+	float slope;
+	int out_f32;
+	int shuffle2;            // ConvTranspose k2s2: channel q*(cout/4)+o -> pixel (2y+q/2, 2x+q%2), channel o
+};
+
+cudaError_t launch_preprocess(const FrameIO *io, const __half *flow_prev, __half *flow_next,
+    int batch, int h, int w, int ph, int pw, int k, int cstride, cudaStream_t s);
+
+cudaError_t launch_conv_simt(const ConvArgs &a, cudaStream_t s);
+// bytes of the SIMT weight layout [tap][cin_padded][cout] fp16
+size_t conv_simt_weight_bytes(int ksize, int cin_padded, int cout);
+void conv_simt_pack_weights(const float *kernel, const float *scale, int ksize, int cin,
+    int cin_padded, int cout, __half *dst);
+
+cudaError_t launch_maxpool2(const __half *in, __half *out, int batch, int h, int w, int c, cudaStream_t s);
+cudaError_t launch_upscale2(const __half *in, __half *out, int batch, int h, int w, int c, cudaStream_t s);
+
+cudaError_t launch_warp_s2d(const __half *pre_gen, const float *flow_head, const FrameIO *io,
+    __half *gen_in, float *taps, const float *brightness, int batch, int h, int w, int ph, int pw,
+    int cstride, cudaStream_t s);
+
+cudaError_t launch_final(const __half *mid, const float *w2, const float *bias2, const FrameIO *io,
+    __half *pre_gen_next, float *out_raw, const float *brightness, int batch, int h, int w,
+    cudaStream_t s);
+
+}  // namespace ju

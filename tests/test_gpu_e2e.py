@@ -1,0 +1,212 @@
+"""End-to-end parity of the runtime entry point (ju_process == the C-ABI twin
+of Runtime::processImage) against the CPU oracle, plus the boundary contract:
+strides, CUDA-resident images, batching, determinism, state handling."""
+
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from joshupscale_b200 import kernels as jk
+from joshupscale_b200 import runtime as jrt
+from joshupscale_b200 import synthetic
+from oracle import reference_graph as og
+from tests.gpu_util import make_model, require_gpu, u8_stats
+
+pytestmark = pytest.mark.gpu
+
+# north star: final image within max-abs 2/255 and >= 45 dB PSNR of the fp32
+# reference graph, fp16 storage on the GPU
+MAX_ABS_FP32 = 2
+MIN_PSNR_DB = 45.0
+
+
+@pytest.fixture(autouse=True, scope="module")
+def _gpu():
+    require_gpu()
+
+
+def _run_gpu(path, frames, batch=1):
+    with jrt.Runtime(path, 0, batch) as rt:
+        return np.stack([rt.process(f) for f in frames])
+
+
+@pytest.mark.parametrize("preset,conditioned,nframes", [
+    ("tiny", True, 6), ("small", True, 6), ("small", False, 4), ("small_resnet", True, 4)])
+def test_recurrent_parity_small(tmp_path, preset, conditioned, nframes):
+    cfg, w, path = make_model(tmp_path, preset, conditioned=conditioned)
+    frames = synthetic.frames(cfg.frame_height, cfg.frame_width, nframes)
+    got = _run_gpu(path, frames)
+    emu, _ = og.Graph(cfg, w, "fp16emu").run(frames)
+    ref, _ = og.Graph(cfg, w, "fp32").run(frames)
+    assert not got[..., 3].any()
+    for t in range(nframes):
+        m16, frac16, _ = u8_stats(got[t, ..., :3], emu[t, ..., :3])
+        m32, _, psnr32 = u8_stats(got[t, ..., :3], ref[t, ..., :3])
+        # against the fp16-emulating oracle only truncation flips remain
+        assert m16 <= 1 and frac16 < 0.02, (t, m16, frac16)
+        assert m32 <= MAX_ABS_FP32 and psnr32 >= MIN_PSNR_DB, (t, m32, psnr32)
+
+
+def test_intermediate_taps_match_oracle(tmp_path):
+    """flow head, generator input and recurrent state after 3 frames."""
+    cfg, w, path = make_model(tmp_path, "small")
+    frames = synthetic.frames(cfg.frame_height, cfg.frame_width, 3)
+    g = og.Graph(cfg, w, "fp16emu")
+    g.keep_taps = True
+    state = g.zero_state()
+    with jrt.Runtime(path) as rt:
+        for t in range(3):
+            out = rt.process(frames[t])
+            want, state, aux = g.step(frames[t:t + 1], state)
+            head = rt.read_tensor("flow_head")
+            np.testing.assert_allclose(head, g.taps["flow/head"].numpy(), rtol=0, atol=5e-3)
+            gen_in = rt.read_tensor("gen_in").astype(np.float32)
+            want_in = g.taps["generator/input"].numpy()
+            assert not gen_in[..., 51:].any()
+            # warp of a slightly different flow: compare loosely, LR channels exactly
+            np.testing.assert_array_equal(gen_in[..., :3], want_in[..., :3])
+            assert np.abs(gen_in[..., 3:51] - want_in[..., 3:]).mean() < 2e-3
+            pre_gen = rt.read_tensor("pre_gen").astype(np.float32)
+            assert np.abs(pre_gen[..., :3] - state["pre_gen"].numpy()).max() < 6e-3
+            flow_in = rt.read_tensor("flow_in").astype(np.float32)
+            want_fi = torch.cat(list(state["last_frames"]), -1).numpy()
+            np.testing.assert_array_equal(flow_in[..., :want_fi.shape[-1]], want_fi)
+
+
+def test_full_size_psp_quality_16_frames(tmp_path):
+    """BASELINE.json config 1: PSP quality, 1 stream, 16 synthetic 480x270 frames."""
+    cfg, w, path = make_model(tmp_path, "psp_quality")
+    frames = synthetic.frames(270, 480, 16)
+    got = _run_gpu(path, frames)
+    ref, _ = og.Graph(cfg, w, "fp32").run(frames)
+    worst_abs, worst_psnr = 0, 1e9
+    for t in range(16):
+        m, _, p = u8_stats(got[t, ..., :3], ref[t, ..., :3])
+        worst_abs, worst_psnr = max(worst_abs, m), min(worst_psnr, p)
+    print(f"PSP quality 16 frames vs fp32 oracle: max-abs {worst_abs}, min PSNR {worst_psnr:.2f} dB")
+    assert worst_abs <= MAX_ABS_FP32 and worst_psnr >= MIN_PSNR_DB
+
+
+def test_adversarial_inputs(tmp_path):
+    cfg, w, path = make_model(tmp_path, "small")
+    for kind in ("black", "white", "checker", "cut"):
+        frames = synthetic.frames(cfg.frame_height, cfg.frame_width, 6, kind=kind)
+        got = _run_gpu(path, frames)
+        ref, _ = og.Graph(cfg, w, "fp32").run(frames)
+        m, _, p = u8_stats(got[..., :3], ref[..., :3])
+        assert m <= MAX_ABS_FP32 and p >= MIN_PSNR_DB, (kind, m, p)
+
+
+def test_bit_stable_and_reset(tmp_path):
+    cfg, w, path = make_model(tmp_path, "small")
+    frames = synthetic.frames(cfg.frame_height, cfg.frame_width, 5)
+    a = _run_gpu(path, frames)
+    b = _run_gpu(path, frames)
+    np.testing.assert_array_equal(a, b)
+    with jrt.Runtime(path) as rt:
+        for f in frames[:3]:
+            rt.process(f)
+        rt.reset_state()
+        c = np.stack([rt.process(f) for f in frames])
+    np.testing.assert_array_equal(a, c)
+
+
+def test_strides_and_bottom_up_images(tmp_path):
+    """Padded and negative strides (AviSynth passes the last row + negative
+    stride, avisynth_plugin/src/main.cc:125-142)."""
+    cfg, w, path = make_model(tmp_path, "small")
+    h, wd = cfg.frame_height, cfg.frame_width
+    frames = synthetic.frames(h, wd, 3)
+    want = _run_gpu(path, frames)
+    lib = jrt.load_library()
+    with jrt.Runtime(path) as rt:
+        for t in range(3):
+            # input: bottom-up with row padding; output: bottom-up with padding
+            in_pitch, out_pitch = wd * 4 + 32, wd * 16 + 64
+            ibuf = np.zeros((h, in_pitch), np.uint8)
+            ibuf[::-1, :wd * 4] = frames[t].reshape(h, wd * 4)
+            obuf = np.full((4 * h, out_pitch), 0xAB, np.uint8)
+            i = jrt.JuImage(ibuf.ctypes.data + (h - 1) * in_pitch, jrt.LOC_CPU, -in_pitch, wd, h)
+            o = jrt.JuImage(obuf.ctypes.data + (4 * h - 1) * out_pitch, jrt.LOC_CPU, -out_pitch, 4 * wd, 4 * h)
+            rt.process_images([i], [o])
+            np.testing.assert_array_equal(obuf[::-1, :wd * 16].reshape(4 * h, 4 * wd, 4), want[t])
+            assert (obuf[:, wd * 16:] == 0xAB).all()  # padding untouched
+
+
+def test_cuda_resident_images(tmp_path):
+    cfg, w, path = make_model(tmp_path, "small")
+    h, wd = cfg.frame_height, cfg.frame_width
+    frames = synthetic.frames(h, wd, 3)
+    want = _run_gpu(path, frames)
+    with jrt.Runtime(path) as rt:
+        d_in = jk.DeviceArray((h, wd, 4), np.uint8)
+        d_out = jk.DeviceArray((4 * h, 4 * wd, 4), np.uint8)
+        for t in range(3):
+            d_in.upload(frames[t])
+            i = jrt.JuImage(d_in.ptr, jrt.LOC_CUDA, wd * 4, wd, h)
+            o = jrt.JuImage(d_out.ptr, jrt.LOC_CUDA, wd * 16, 4 * wd, 4 * h)
+            rt.process_images([i], [o])
+            np.testing.assert_array_equal(d_out.download(), want[t])
+
+
+def test_batched_streams_equal_single_streams(tmp_path):
+    """N independent streams in lockstep == each stream alone (bit-exact)."""
+    cfg, w, path = make_model(tmp_path, "small")
+    h, wd = cfg.frame_height, cfg.frame_width
+    streams = [synthetic.frames(h, wd, 4, stream_id=s) for s in range(3)]
+    singles = [_run_gpu(path, s) for s in streams]
+    with jrt.Runtime(path, 0, 3) as rt:
+        for t in range(4):
+            outs = rt.process_batch([s[t] for s in streams])
+            for s in range(3):
+                np.testing.assert_array_equal(outs[s], singles[s][t])
+
+
+def test_errors_leave_state_untouched(tmp_path):
+    cfg, w, path = make_model(tmp_path, "small")
+    h, wd = cfg.frame_height, cfg.frame_width
+    frames = synthetic.frames(h, wd, 3)
+    want = _run_gpu(path, frames)
+    with jrt.Runtime(path) as rt:
+        np.testing.assert_array_equal(rt.process(frames[0]), want[0])
+        with pytest.raises(jrt.JoshUpscaleError, match="size"):
+            rt.process(np.zeros((h + 1, wd, 4), np.uint8))
+        bad = jrt.JuImage(1, jrt.LOC_GRAPHICS_RESOURCE, 0, wd, h)
+        good = jrt._image(np.empty(rt.out_shape, np.uint8), 0, 0)
+        with pytest.raises(jrt.JoshUpscaleError, match="GRAPHICS_RESOURCE"):
+            rt.process_images([bad], [good])
+        np.testing.assert_array_equal(rt.process(frames[1]), want[1])
+
+
+def test_session_mirror_of_reference_driver(tmp_path):
+    cfg, w, path = make_model(tmp_path, "small")
+    frames = synthetic.frames(cfg.frame_height, cfg.frame_width, 2)
+    want = _run_gpu(path, frames)
+    sess = jrt.Session(path)
+    for t in range(2):
+        np.testing.assert_array_equal(sess.run(frames[t][..., :3]), want[t][..., :3])
+
+
+def test_cxx_api_like_the_plugins(tmp_path):
+    """Compile a caller against include/JoshUpscale/core.h (the header the
+    AviSynth/OBS plugins include) and check it produces the same bytes."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg, w, path = make_model(tmp_path, "small")
+    frames = synthetic.frames(cfg.frame_height, cfg.frame_width, 3)
+    want = _run_gpu(path, frames)
+    exe = str(tmp_path / "api_smoke")
+    libdir = os.path.dirname(jrt.library_path())
+    subprocess.run(["g++", "-std=c++20", "-O1", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "tests", "cxx", "api_smoke.cc"), "-o", exe,
+                    "-L", libdir, "-lJoshUpscale", f"-Wl,-rpath,{libdir}"], check=True)
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    frames.tofile(fin)
+    r = subprocess.run([exe, path, fin, "3", fout], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ModelException" in r.stdout and "model.jup" in r.stdout
+    got = np.fromfile(fout, np.uint8).reshape(want.shape)
+    np.testing.assert_array_equal(got, want)
