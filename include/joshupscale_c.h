@@ -131,6 +131,15 @@ JU_API int ju_launch_conv(int impl, const void *in, const void *weights, const f
 JU_API int64_t ju_pack_conv_weights(int impl, const float *kernel, const float *scale,
     int ksize, int cin, int cin_padded, int cout, void *dst);
 
+/* Global integer options: "tc_variant" (tcgen05 conv halo/descriptor variant,
+ * see conv_tc.cu; bits 0-1 halo layout, bit 2 base-offset mode). */
+JU_API int ju_set_option(const char *key, int value);
+
+/* Stand-alone timing of one convolution shape: allocates its own buffers,
+ * launches `iters` times back to back and returns the mean device time. */
+JU_API int ju_bench_conv(int impl, int batch, int h, int w, int cin, int cout, int ksize,
+    int with_residual, int iters, double *usec);
+
 JU_API int ju_launch_maxpool2(const void *in, void *out, int batch, int h, int w, int c, void *stream);
 JU_API int ju_launch_upscale2(const void *in, void *out, int batch, int h, int w, int c, void *stream);
 

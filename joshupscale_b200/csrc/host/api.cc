@@ -344,17 +344,96 @@ int ju_launch_conv(int impl, const void *in, const void *weights, const float *b
 		a.slope = slope;
 		a.out_f32 = out_f32;
 		a.shuffle2 = shuffle2;
-		if (impl != 0) throw std::invalid_argument("unknown conv impl");
-		JU_CUDA(ju::launch_conv_simt(a, static_cast<cudaStream_t>(stream)));
+		auto s = static_cast<cudaStream_t>(stream);
+		if (impl == 0) {
+			JU_CUDA(ju::launch_conv_simt(a, s));
+		} else if (impl == 1) {
+			ju::ConvTcLaunch l;
+			JU_CUDA(ju::conv_tc_prepare(a, ju::conv_tc_get_variant(), &l));
+			JU_CUDA(ju::conv_tc_launch(l, nullptr, s));
+		} else {
+			throw std::invalid_argument("unknown conv impl");
+		}
+	});
+}
+
+int ju_set_option(const char *key, int value) {
+	return guarded([&] {
+		if (!key) throw std::invalid_argument("null key");
+		if (std::strcmp(key, "tc_variant") == 0) {
+			ju::conv_tc_set_variant(value);
+		} else {
+			throw std::invalid_argument(std::string("unknown option ") + key);
+		}
+	});
+}
+
+int ju_bench_conv(int impl, int batch, int h, int w, int cin, int cout, int ksize, int with_residual,
+    int iters, double *usec) {
+	return guarded([&] {
+		requireDevice();
+		if (!usec || iters < 1) throw std::invalid_argument("bad arguments");
+		const int cs = (cin + 63) / 64 * 64, os = (cout + 63) / 64 * 64;
+		const size_t px = static_cast<size_t>(batch) * h * w;
+		ju::DeviceBuffer in(px * cs * 2), out(px * os * 2), res(px * os * 2), bias(cout * 4);
+		JU_CUDA(cudaMemset(in.get(), 0x2c, in.bytes()));   // fp16 0x2c2c ~ 0.065
+		JU_CUDA(cudaMemset(res.get(), 0x2c, res.bytes()));
+		const int cinp = impl == 1 ? cs : (cin + 15) / 16 * 16;
+		ju::DeviceBuffer wts(static_cast<size_t>(ksize) * ksize * cinp * cout * 2);
+		JU_CUDA(cudaMemset(wts.get(), 0x24, wts.bytes()));  // ~0.016
+		ju::ConvArgs a{};
+		a.in = in.as<__half>();
+		a.weights = wts.get();
+		a.bias = bias.as<float>();
+		a.residual = with_residual ? res.as<__half>() : nullptr;
+		a.out = out.get();
+		a.batch = batch;
+		a.h = h;
+		a.w = w;
+		a.cin_stride = cs;
+		a.cin = cinp;
+		a.cout = cout;
+		a.cout_stride = os;
+		a.ksize = ksize;
+		a.act = ju::ACT_RELU;
+		cudaEvent_t e0, e1;
+		JU_CUDA(cudaEventCreate(&e0));
+		JU_CUDA(cudaEventCreate(&e1));
+		ju::ConvTcLaunch l;
+		if (impl == 1) JU_CUDA(ju::conv_tc_prepare(a, ju::conv_tc_get_variant(), &l));
+		auto launch = [&] {
+			if (impl == 1) {
+				JU_CUDA(ju::conv_tc_launch(l, nullptr, nullptr));
+			} else {
+				JU_CUDA(ju::launch_conv_simt(a, nullptr));
+			}
+		};
+		for (int i = 0; i < 3; ++i) launch();
+		JU_CUDA(cudaEventRecord(e0, nullptr));
+		for (int i = 0; i < iters; ++i) launch();
+		JU_CUDA(cudaEventRecord(e1, nullptr));
+		JU_CUDA(cudaEventSynchronize(e1));
+		float ms = 0.f;
+		JU_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+		cudaEventDestroy(e0);
+		cudaEventDestroy(e1);
+		*usec = ms * 1000.0 / iters;
 	});
 }
 
 int64_t ju_pack_conv_weights(int impl, const float *kernel, const float *scale, int ksize, int cin,
     int cin_padded, int cout, void *dst) {
-	if (impl != 0) return -1;
-	auto bytes = static_cast<int64_t>(ju::conv_simt_weight_bytes(ksize, cin_padded, cout));
-	if (dst) ju::conv_simt_pack_weights(kernel, scale, ksize, cin, cin_padded, cout, static_cast<__half *>(dst));
-	return bytes;
+	if (impl == 0) {
+		auto bytes = static_cast<int64_t>(ju::conv_simt_weight_bytes(ksize, cin_padded, cout));
+		if (dst) ju::conv_simt_pack_weights(kernel, scale, ksize, cin, cin_padded, cout, static_cast<__half *>(dst));
+		return bytes;
+	}
+	if (impl == 1 && cin_padded % 64 == 0) {
+		auto bytes = static_cast<int64_t>(ju::conv_tc_weight_bytes(ksize, cin_padded, cout));
+		if (dst) ju::conv_tc_pack_weights(kernel, scale, ksize, cin, cin_padded, cout, static_cast<__half *>(dst));
+		return bytes;
+	}
+	return -1;
 }
 
 int ju_launch_maxpool2(const void *in, void *out, int batch, int h, int w, int c, void *stream) {

@@ -32,6 +32,7 @@ Engine::Engine(const ModelFile &model, int device, int batch)
 		            << "; kernels are built for sm_100a only";
 	}
 	m_ConvImpl = envInt("JU_CONV_IMPL", 0);
+	if (const char *v = std::getenv("JU_TC_VARIANT")) conv_tc_set_variant(std::atoi(v));
 	m_UseGraph = envInt("JU_NO_GRAPH", 0) == 0;
 	JU_CUDA(cudaStreamCreateWithFlags(&m_Stream, cudaStreamNonBlocking));
 	try {
@@ -52,7 +53,8 @@ Engine::Engine(const ModelFile &model, int device, int batch)
 	}
 	JU_LOG_INFO << "engine ready: " << m_Spec.frameW << "x" << m_Spec.frameH << " -> "
 	            << 4 * m_Spec.frameW << "x" << 4 * m_Spec.frameH << ", batch " << m_Batch << ", "
-	            << m_Plans[0].size() << " kernels/frame, conv impl " << m_ConvImpl;
+	            << m_Plans[0].size() << " kernels/frame, conv impl " << m_ConvImpl << " (" << m_TcOps / 2
+	            << " tcgen05 launches/frame)";
 }
 
 Engine::~Engine() {
@@ -83,6 +85,23 @@ ConvLayer *Engine::addConv(const std::string &name, const FoldedConv &f, int act
 	    packed.data());
 	layer->wSimt = DeviceBuffer(packed.size() * sizeof(__half));
 	layer->wSimt.upload(packed.data(), packed.size() * sizeof(__half));
+	{
+		// tcgen05 layout: Cin padded to the 64-channel K block of the activation buffers
+		const int cinTc = pad64(f.cin);
+		ConvArgs shape{};
+		shape.ksize = f.ksize;
+		shape.cin_stride = cinTc;
+		shape.cin = cinTc;
+		shape.cout = f.cout;
+		shape.cout_stride = 8;
+		shape.shuffle2 = shuffle2 ? 1 : 0;
+		if (conv_tc_supported(shape)) {
+			std::vector<__half> tc(conv_tc_weight_bytes(f.ksize, cinTc, f.cout) / sizeof(__half));
+			conv_tc_pack_weights(f.kernel.data(), f.scale.data(), f.ksize, f.cin, cinTc, f.cout, tc.data());
+			layer->wTc = DeviceBuffer(tc.size() * sizeof(__half));
+			layer->wTc.upload(tc.data(), tc.size() * sizeof(__half));
+		}
+	}
 	layer->bias = DeviceBuffer(f.bias.size() * sizeof(float));
 	layer->bias.upload(f.bias.data(), f.bias.size() * sizeof(float));
 	ConvLayer *raw = layer.get();
@@ -160,6 +179,7 @@ void Engine::registerTensor(const std::string &name, void *p0, void *p1, int dty
 void Engine::allocate() {
 	const ModelSpec &s = m_Spec;
 	const std::uint64_t B = m_Batch, H = s.frameH, W = s.frameW, PH = s.padH, PW = s.padW;
+	m_TcError = DeviceBuffer(sizeof(int));
 	m_IoHost = PinnedBuffer(sizeof(FrameIO) * B);
 	m_IoDev = DeviceBuffer(sizeof(FrameIO) * B);
 	m_InStage = DeviceBuffer(B * H * W * 4);
@@ -230,6 +250,19 @@ Op Engine::convOp(ConvLayer *L, const __half *in, int cinStride, const __half *r
 	op.flops = 2.0 * m_Batch * h * w * L->ksize * L->ksize * L->cinReal * L->cout;
 	op.bytes = static_cast<double>(m_Batch) * h * w *
 	           (L->cinReal * 2.0 + L->cout * (outF32 ? 4.0 : 2.0) + (residual ? L->cout * 2.0 : 0.0));
+	if (m_ConvImpl == 1 && L->wTc.get()) {
+		ConvArgs t = a;
+		t.weights = L->wTc.get();
+		t.cin = pad64(L->cinReal);
+		if (t.cin <= cinStride && conv_tc_supported(t)) {
+			ConvTcLaunch launch;
+			checkCuda(conv_tc_prepare(t, conv_tc_get_variant(), &launch), "conv_tc_prepare");
+			int *err = m_TcError.as<int>();
+			op.run = [launch, err](cudaStream_t s) { return conv_tc_launch(launch, err, s); };
+			++m_TcOps;
+			return op;
+		}
+	}
 	op.run = [a](cudaStream_t s) { return launch_conv_simt(a, s); };
 	return op;
 }

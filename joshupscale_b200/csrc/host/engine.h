@@ -98,6 +98,8 @@ private:
 
 	PinnedBuffer m_IoHost;
 	DeviceBuffer m_IoDev;
+	DeviceBuffer m_TcError;
+	int m_TcOps = 0;
 	DeviceBuffer m_InStage, m_OutStage;
 	std::vector<ju_image> m_LastOutputs;
 	std::vector<bool> m_OutputNeedsCopy;

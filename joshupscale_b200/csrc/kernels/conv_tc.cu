@@ -1,0 +1,605 @@
+// Implicit-GEMM 3x3 / 1x1 convolution on the 5th-generation tensor cores
+// (tcgen05.mma, accumulators in TMEM, operands staged by TMA) for sm_100a.
+//
+// Replaces, inside the reference's TensorRT engine, layers.Conv2D(3x3/1x1,
+// SAME) + BatchNormalization + activation (+ Add) - the ResBlock stack that is
+// 91% of the frame's MACs (scripts/training/models.py:193-254, 531-550), the
+// flow net's convs (models.py:257-331, 377-479) and Conv2DTranspose(k2,s2) as
+// a 1x1 GEMM with a pixel-shuffle store (models.py:559-572).
+//
+// GEMM view: D[128 pixels, N=Cout tile] += A[128 pixels, 64 ch] * B[64 ch, N],
+// looped over the 9 taps and Cin/64 channel blocks, fp16 operands, fp32
+// accumulation in TMEM.
+//
+// Data movement (the B200-specific part):
+//  * An M tile is a 16-row x 8-column pixel patch.  One TMA box load brings its
+//    (16+2) x (8+2) halo of 64-channel pixels (128 B each, 128B-swizzled) into
+//    shared memory ONCE; all 9 taps are then expressed as UMMA shared-memory
+//    descriptors into that same halo tile: an 8-row core-matrix group is 8
+//    horizontally adjacent pixels (8 x 128 B contiguous), consecutive groups
+//    are consecutive image rows (stride = halo pitch), and a tap (dy, dx) only
+//    shifts the descriptor start address by (dy*pitch + dx) * 128 B.  L2->SMEM
+//    traffic is 1.4x the activation tensor instead of 9x (im2col-style loads).
+//  * SAME zero padding and ragged right/bottom edges come from TMA out-of-bounds
+//    zero fill (negative / past-the-end box coordinates); masked in the store.
+//  * Weights (B operand) stay resident in shared memory for the whole
+//    persistent CTA when they fit (64->64: 72 KB), else stream with the halo.
+//  * Warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one elected
+//    thread) + TMEM allocator, warps 2-5 = epilogue (tcgen05.ld -> +bias
+//    [folded BN] -> +residual -> ReLU/LeakyReLU -> fp16/fp32 store); two TMEM
+//    accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cuda.h>
+
+#include <cstring>
+
+#include "kernels.h"
+
+namespace ju {
+
+namespace {
+
+constexpr int kTileH = 16;  // pixel rows per M tile (= UMMA core-matrix groups)
+constexpr int kTileW = 8;   // pixel columns per M tile (= rows per core-matrix group)
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr uint32_t kSmemLimit = 227 * 1024;
+
+struct TcParams {
+	int batch, h, w;
+	int tiles_x, tiles_y, n_tiles, total_tiles;
+	int kb;      // Cin / 64
+	int ks;      // 1 or 3
+	int nt;      // N tile (32 or 64)
+	int cout, cout_stride;
+	int pitch;   // halo pitch in pixels
+	int nbox;    // 1, or 3 = one 8-wide box per horizontal tap (canonical 1024B-aligned starts)
+	int base_off_mode;
+	int b_resident;
+	int stages;
+	uint32_t a_box_bytes, a_region_bytes, stage_bytes, b_slice_bytes;
+	const float *bias;
+	const __half *residual;
+	void *out;
+	int act;
+	float slope;
+	int out_f32;
+	int shuffle2;
+	int *error_flag;
+};
+
+// ---- PTX helpers ----------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+	return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+	uint32_t ok;
+	asm volatile(
+	    "{\n\t.reg .pred p;\n\t"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+	    "selp.u32 %0, 1, 0, p;\n\t}"
+	    : "=r"(ok)
+	    : "r"(bar), "r"(parity)
+	    : "memory");
+	return ok;
+}
+
+// Bounded wait: a protocol bug must surface as an error, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int *error_flag, int code) {
+	for (uint32_t i = 0; i < (1u << 22); ++i) {
+		if (mbar_try_wait(bar, parity)) return;
+		if (i > 128) __nanosleep(128);
+	}
+	if (error_flag) atomicExch(error_flag, code);
+	__trap();
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0,
+    int c1, int c2, int c3) {
+	asm volatile(
+	    "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+	    " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+	    "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+	    : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0,
+    int c1) {
+	asm volatile(
+	    "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+	    " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+	    "l"(map), "r"(bar), "r"(c0), "r"(c1)
+	    : "memory");
+}
+
+__device__ __forceinline__ void tcgen05_fence_before() {
+	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+	asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+	             : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (fp16 in, fp32 accumulate)
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+    uint32_t accumulate) {
+	asm volatile(
+	    "{\n\t.reg .pred p;\n\t"
+	    "setp.ne.b32 p, %4, 0;\n\t"
+	    "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+	    "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+	    : "memory");
+}
+
+// UMMA shared-memory matrix descriptor, K-major, SWIZZLE_128B (cute
+// UMMA::SmemDescriptor bit layout): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), base_offset [49,52), layout [61,64).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t base_off) {
+	uint64_t d = 0;
+	d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+	d |= static_cast<uint64_t>(1) << 16;
+	d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+	d |= static_cast<uint64_t>(1) << 46;
+	d |= static_cast<uint64_t>(base_off & 7u) << 49;
+	d |= static_cast<uint64_t>(2) << 61;
+	return d;
+}
+
+// Instruction descriptor, kind::f16: D fp32, A/B fp16, both K-major, M=128.
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+	return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+	asm volatile(
+	    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+	    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+	    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+	    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+	      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+	      "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+	      "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+	      "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+	    : "r"(taddr)
+	    : "memory");
+	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct TileCoord {
+	int b, y0, x0, n0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const TcParams &p, int idx) {
+	TileCoord t;
+	int nt_idx = idx % p.n_tiles;
+	int rest = idx / p.n_tiles;
+	int tx = rest % p.tiles_x;
+	rest /= p.tiles_x;
+	int ty = rest % p.tiles_y;
+	t.b = rest / p.tiles_y;
+	t.y0 = ty * kTileH;
+	t.x0 = tx * kTileW;
+	t.n0 = nt_idx * p.nt;
+	return t;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+    const TcParams p) {
+	extern __shared__ uint8_t smem_raw[];
+	// SWIZZLE_128B operands need 1024-byte aligned tiles
+	const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+	const int taps = p.ks * p.ks;
+	const uint32_t stages_bytes = static_cast<uint32_t>(p.stages) * p.stage_bytes;
+	const uint32_t resb_base = smem_base + stages_bytes;
+	const uint32_t resb_bytes = p.b_resident ? static_cast<uint32_t>(taps * p.kb) * p.b_slice_bytes : 0u;
+	const uint32_t bar_base = resb_base + resb_bytes;  // 8-byte aligned (all sizes are multiples of 1024)
+	auto full_bar = [&](int s) { return bar_base + 8u * s; };
+	auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+	auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
+	auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 2 + s); };
+	const uint32_t w_bar = bar_base + 8u * (2 * kMaxStages + 4);
+	const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 5);
+
+	const int warp = threadIdx.x >> 5;
+	const int lane = threadIdx.x & 31;
+	const uint32_t tmem_cols = p.nt * 2 <= 64 ? 64u : 128u;
+
+	if (warp == 0 && lane == 0) {
+		for (int s = 0; s < p.stages; ++s) {
+			mbar_init(full_bar(s), 1);
+			mbar_init(empty_bar(s), 1);
+		}
+		for (int s = 0; s < 2; ++s) {
+			mbar_init(tfull_bar(s), 1);
+			mbar_init(tempty_bar(s), 4);  // one arrival per epilogue warp
+		}
+		mbar_init(w_bar, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	if (warp == 1) {
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+		             "r"(tmem_cols)
+		             : "memory");
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+	}
+	tcgen05_fence_before();
+	__syncthreads();
+	tcgen05_fence_after();
+	uint32_t tmem_base;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+	const int pad = (p.ks - 1) / 2;
+	const int halo_h = kTileH + p.ks - 1;
+	(void) halo_h;
+
+	if (warp == 0) {
+		// ===================== TMA producer =====================
+		if (lane == 0) {
+			if (p.b_resident) {
+				mbar_arrive_expect_tx(w_bar, resb_bytes);
+				for (int s = 0; s < taps * p.kb; ++s) {
+					// slice s = tap * kb + kbi ; rows [s*cout, s*cout + nt)
+					tma_load_2d(resb_base + s * p.b_slice_bytes, &map_b, w_bar, 0, s * p.cout);
+				}
+			}
+			int it = 0;
+			for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+				const TileCoord t = decode_tile(p, tile);
+				for (int kbi = 0; kbi < p.kb; ++kbi, ++it) {
+					const int s = it % p.stages;
+					const uint32_t ph = (it / p.stages) & 1;
+					mbar_wait(empty_bar(s), ph ^ 1u, p.error_flag, 1);
+					const uint32_t stage = smem_base + s * p.stage_bytes;
+					const uint32_t bytes = p.nbox * p.a_box_bytes + (p.b_resident ? 0u : taps * p.b_slice_bytes);
+					mbar_arrive_expect_tx(full_bar(s), bytes);
+					for (int bx = 0; bx < p.nbox; ++bx) {
+						tma_load_4d(stage + bx * p.a_box_bytes, &map_a, full_bar(s), kbi * 64,
+						    t.x0 - pad + (p.nbox == 3 ? bx : 0), t.y0 - pad, t.b);
+					}
+					if (!p.b_resident) {
+						for (int tap = 0; tap < taps; ++tap) {
+							tma_load_2d(stage + p.a_region_bytes + tap * p.b_slice_bytes, &map_b, full_bar(s), 0,
+							    (tap * p.kb + kbi) * p.cout + t.n0);
+						}
+					}
+				}
+			}
+		}
+	} else if (warp == 1) {
+		// ===================== MMA issuer =====================
+		if (lane == 0) {
+			const uint32_t idesc = make_idesc(p.nt);
+			const uint32_t a_sbo = static_cast<uint32_t>(p.pitch) * 128u;
+			if (p.b_resident) {
+				mbar_wait(w_bar, 0, p.error_flag, 2);
+			}
+			int it = 0, tcount = 0;
+			for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+				const int as = tcount & 1;
+				const uint32_t aph = (tcount >> 1) & 1;
+				mbar_wait(tempty_bar(as), aph ^ 1u, p.error_flag, 3);
+				tcgen05_fence_after();
+				const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.nt);
+				for (int kbi = 0; kbi < p.kb; ++kbi, ++it) {
+					const int s = it % p.stages;
+					const uint32_t ph = (it / p.stages) & 1;
+					mbar_wait(full_bar(s), ph, p.error_flag, 4);
+					tcgen05_fence_after();
+					const uint32_t stage = smem_base + s * p.stage_bytes;
+					for (int tap = 0; tap < taps; ++tap) {
+						const int dy = tap / p.ks, dx = tap % p.ks;
+						uint32_t a_addr;
+						if (p.nbox == 3) {
+							a_addr = stage + dx * p.a_box_bytes + dy * p.pitch * 128;
+						} else {
+							a_addr = stage + (dy * p.pitch + dx) * 128;
+						}
+						const uint32_t b_addr = p.b_resident
+						                            ? resb_base + (tap * p.kb + kbi) * p.b_slice_bytes
+						                            : stage + p.a_region_bytes + tap * p.b_slice_bytes;
+						const uint32_t boff = p.base_off_mode ? ((a_addr >> 7) & 7u) : 0u;
+#pragma unroll
+						for (int k16 = 0; k16 < 4; ++k16) {
+							const uint64_t a_desc = make_smem_desc(a_addr + k16 * 32, a_sbo, boff);
+							const uint64_t b_desc = make_smem_desc(b_addr + k16 * 32, 1024u, 0u);
+							umma_f16(d_tmem, a_desc, b_desc, idesc, (kbi | tap | k16) != 0 ? 1u : 0u);
+						}
+					}
+					umma_commit(empty_bar(s));  // frees the stage when these MMAs have read it
+				}
+				umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
+			}
+		}
+	} else {
+		// ===================== epilogue (warps 2..5) =====================
+		const int q = warp & 3;  // TMEM lane quarter this warp may access
+		const int row = q * 32 + lane;
+		const int cpp = p.shuffle2 ? p.cout / 4 : p.cout;  // channels per output pixel
+		int tcount = 0;
+		for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+			const TileCoord t = decode_tile(p, tile);
+			const int as = tcount & 1;
+			const uint32_t aph = (tcount >> 1) & 1;
+			mbar_wait(tfull_bar(as), aph, p.error_flag, 5);
+			tcgen05_fence_after();
+			const int y = t.y0 + (row >> 3), x = t.x0 + (row & 7);
+			const bool valid = y < p.h && x < p.w;
+			for (int half = 0; half < p.nt / 32; ++half) {
+				uint32_t acc[32];
+				const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+				                       static_cast<uint32_t>(as * p.nt + half * 32);
+				tmem_ld32(taddr, acc);
+				if (!valid) continue;
+				const int co = t.n0 + half * 32;  // first of 32 consecutive output channels
+				size_t opix;
+				int oc;
+				if (p.shuffle2) {
+					const int sub = co / cpp;
+					oc = co % cpp;
+					opix = (static_cast<size_t>(t.b) * 2 * p.h + 2 * y + (sub >> 1)) * 2 * p.w + 2 * x + (sub & 1);
+				} else {
+					oc = co;
+					opix = (static_cast<size_t>(t.b) * p.h + y) * p.w + x;
+				}
+				float v[32];
+#pragma unroll
+				for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(acc[c]);
+				if (p.bias) {
+					const float4 *bp = reinterpret_cast<const float4 *>(p.bias + co);
+#pragma unroll
+					for (int c4 = 0; c4 < 8; ++c4) {
+						const float4 bv = __ldg(bp + c4);
+						v[c4 * 4 + 0] += bv.x;
+						v[c4 * 4 + 1] += bv.y;
+						v[c4 * 4 + 2] += bv.z;
+						v[c4 * 4 + 3] += bv.w;
+					}
+				}
+				if (p.residual) {
+					const uint4 *rp = reinterpret_cast<const uint4 *>(p.residual + opix * p.cout_stride + oc);
+#pragma unroll
+					for (int c8 = 0; c8 < 4; ++c8) {
+						const uint4 rv = __ldg(rp + c8);
+						const __half2 *h2 = reinterpret_cast<const __half2 *>(&rv);
+#pragma unroll
+						for (int e = 0; e < 4; ++e) {
+							const float2 f = __half22float2(h2[e]);
+							v[c8 * 8 + e * 2] += f.x;
+							v[c8 * 8 + e * 2 + 1] += f.y;
+						}
+					}
+				}
+				if (p.act == ACT_RELU) {
+#pragma unroll
+					for (int c = 0; c < 32; ++c) v[c] = fmaxf(v[c], 0.f);
+				} else if (p.act == ACT_LRELU) {
+#pragma unroll
+					for (int c = 0; c < 32; ++c) v[c] = v[c] >= 0.f ? v[c] : v[c] * p.slope;
+				}
+				if (p.out_f32) {
+					float4 *op = reinterpret_cast<float4 *>(static_cast<float *>(p.out) + opix * p.cout_stride + oc);
+#pragma unroll
+					for (int c4 = 0; c4 < 8; ++c4) {
+						op[c4] = make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
+					}
+				} else {
+					uint4 *op = reinterpret_cast<uint4 *>(static_cast<__half *>(p.out) + opix * p.cout_stride + oc);
+#pragma unroll
+					for (int c8 = 0; c8 < 4; ++c8) {
+						uint4 o;
+						__half2 h0 = __floats2half2_rn(v[c8 * 8 + 0], v[c8 * 8 + 1]);
+						__half2 h1 = __floats2half2_rn(v[c8 * 8 + 2], v[c8 * 8 + 3]);
+						__half2 h2 = __floats2half2_rn(v[c8 * 8 + 4], v[c8 * 8 + 5]);
+						__half2 h3 = __floats2half2_rn(v[c8 * 8 + 6], v[c8 * 8 + 7]);
+						o.x = *reinterpret_cast<uint32_t *>(&h0);
+						o.y = *reinterpret_cast<uint32_t *>(&h1);
+						o.z = *reinterpret_cast<uint32_t *>(&h2);
+						o.w = *reinterpret_cast<uint32_t *>(&h3);
+						op[c8] = o;
+					}
+				}
+			}
+			// all of this warp's TMEM reads are complete (wait::ld) -> release the stage
+			tcgen05_fence_before();
+			__syncwarp();
+			if (lane == 0) mbar_arrive(tempty_bar(as));
+		}
+	}
+
+	tcgen05_fence_before();
+	__syncthreads();
+	if (warp == 1) {
+		tcgen05_fence_after();
+		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols)
+		             : "memory");
+	}
+}
+
+// ---- host side --------------------------------------------------------------
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encodeTiled() {
+	static EncodeTiledFn fn = nullptr;
+	if (!fn) {
+		void *p = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+		    q != cudaDriverEntryPointSuccess) {
+			return nullptr;
+		}
+		fn = reinterpret_cast<EncodeTiledFn>(p);
+	}
+	return fn;
+}
+
+int g_TcVariant = 0;
+
+}  // namespace
+
+void conv_tc_set_variant(int v) { g_TcVariant = v; }
+int conv_tc_get_variant() { return g_TcVariant; }
+
+bool conv_tc_supported(const ConvArgs &a) {
+	if (a.ksize != 1 && a.ksize != 3) return false;
+	if (a.cin_stride % 64 || a.cin % 64 || a.cin > a.cin_stride) return false;
+	if (a.cout % 32) return false;
+	if (a.cout > 64 && a.cout % 64) return false;
+	if (a.cout_stride % 8) return false;
+	if (a.shuffle2 && (a.cout / 4) % 32) return false;
+	return true;
+}
+
+size_t conv_tc_weight_bytes(int ksize, int cin_padded, int cout) {
+	return static_cast<size_t>(ksize) * ksize * cin_padded * cout * sizeof(__half);
+}
+
+// kernel: Keras (kh, kw, Cin, Cout) fp32 -> [tap][kb][cout][64] fp16 (K-major B slices)
+void conv_tc_pack_weights(const float *kernel, const float *scale, int ksize, int cin, int cin_padded,
+    int cout, __half *dst) {
+	std::memset(dst, 0, conv_tc_weight_bytes(ksize, cin_padded, cout));
+	const int kb = cin_padded / 64;
+	for (int tap = 0; tap < ksize * ksize; ++tap) {
+		for (int c = 0; c < cin; ++c) {
+			for (int o = 0; o < cout; ++o) {
+				float v = kernel[(static_cast<size_t>(tap) * cin + c) * cout + o];
+				if (scale) v = v * scale[o];
+				const size_t idx = ((static_cast<size_t>(tap) * kb + c / 64) * cout + o) * 64 + (c % 64);
+				dst[idx] = __float2half_rn(v);
+			}
+		}
+	}
+}
+
+cudaError_t conv_tc_prepare(const ConvArgs &a, int variant, ConvTcLaunch *out) {
+	if (!conv_tc_supported(a)) return cudaErrorInvalidValue;
+	EncodeTiledFn encode = encodeTiled();
+	if (!encode) return cudaErrorNotSupported;
+	static_assert(sizeof(TcParams) <= sizeof(out->params), "ConvTcLaunch::params too small");
+	static_assert(sizeof(CUtensorMap) == 128, "unexpected CUtensorMap size");
+	TcParams p{};
+	p.batch = a.batch;
+	p.h = a.h;
+	p.w = a.w;
+	p.tiles_x = (a.w + kTileW - 1) / kTileW;
+	p.tiles_y = (a.h + kTileH - 1) / kTileH;
+	p.nt = a.cout >= 64 ? 64 : a.cout;
+	p.n_tiles = a.cout / p.nt;
+	p.total_tiles = a.batch * p.tiles_x * p.tiles_y * p.n_tiles;
+	p.kb = a.cin / 64;
+	p.ks = a.ksize;
+	p.cout = a.cout;
+	p.cout_stride = a.cout_stride;
+	const int taps = a.ksize * a.ksize;
+	const int halo_h = kTileH + a.ksize - 1;
+	const int pitch_mode = variant & 3;
+	p.base_off_mode = (variant >> 2) & 1;
+	if (a.ksize == 1) {
+		p.pitch = kTileW;
+		p.nbox = 1;
+	} else if (pitch_mode == 0) {
+		p.pitch = kTileW + 2;
+		p.nbox = 1;
+	} else if (pitch_mode == 1) {
+		p.pitch = 16;
+		p.nbox = 1;
+	} else {
+		p.pitch = kTileW;
+		p.nbox = 3;
+	}
+	p.a_box_bytes = static_cast<uint32_t>(halo_h * p.pitch * 128);
+	p.a_region_bytes = (p.nbox * p.a_box_bytes + 1023u) & ~1023u;
+	p.b_slice_bytes = static_cast<uint32_t>(p.nt * 128);
+	const uint32_t all_b = static_cast<uint32_t>(taps * p.kb) * p.b_slice_bytes;
+	p.b_resident = (p.n_tiles == 1 && all_b <= 96 * 1024) ? 1 : 0;
+	p.stage_bytes = p.a_region_bytes + (p.b_resident ? 0u : taps * p.b_slice_bytes);
+	const uint32_t fixed = 1024u + 256u + (p.b_resident ? all_b : 0u);
+	int stages = static_cast<int>((kSmemLimit - fixed) / p.stage_bytes);
+	if (stages > kMaxStages) stages = kMaxStages;
+	if (stages < 2) return cudaErrorInvalidValue;
+	p.stages = stages;
+	p.bias = a.bias;
+	p.residual = a.residual;
+	p.out = a.out;
+	p.act = a.act;
+	p.slope = a.slope;
+	p.out_f32 = a.out_f32;
+	p.shuffle2 = a.shuffle2;
+	p.error_flag = nullptr;
+
+	CUtensorMap mapA, mapB;
+	{
+		cuuint64_t dims[4] = {static_cast<cuuint64_t>(a.cin_stride), static_cast<cuuint64_t>(a.w),
+		    static_cast<cuuint64_t>(a.h), static_cast<cuuint64_t>(a.batch)};
+		cuuint64_t strides[3] = {static_cast<cuuint64_t>(a.cin_stride) * 2,
+		    static_cast<cuuint64_t>(a.w) * a.cin_stride * 2,
+		    static_cast<cuuint64_t>(a.h) * a.w * a.cin_stride * 2};
+		cuuint32_t box[4] = {64, static_cast<cuuint32_t>(p.pitch), static_cast<cuuint32_t>(halo_h), 1};
+		cuuint32_t estr[4] = {1, 1, 1, 1};
+		CUresult r = encode(&mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half *>(a.in), dims, strides,
+		    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+		    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+		if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+	}
+	{
+		cuuint64_t dims[2] = {64, static_cast<cuuint64_t>(taps) * p.kb * a.cout};
+		cuuint64_t strides[1] = {128};
+		cuuint32_t box[2] = {64, static_cast<cuuint32_t>(p.nt)};
+		cuuint32_t estr[2] = {1, 1};
+		CUresult r = encode(&mapB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(a.weights), dims, strides,
+		    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+		    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+		if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+	}
+	std::memcpy(out->map_a, &mapA, 128);
+	std::memcpy(out->map_b, &mapB, 128);
+	std::memcpy(out->params, &p, sizeof(p));
+	int dev = 0, sms = 148;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	out->grid = p.total_tiles < sms ? p.total_tiles : sms;
+	out->smem_bytes = 1024u + static_cast<uint32_t>(p.stages) * p.stage_bytes + (p.b_resident ? all_b : 0u) + 256u;
+	return cudaSuccess;
+}
+
+cudaError_t conv_tc_launch(const ConvTcLaunch &l, int *error_flag, cudaStream_t s) {
+	static bool attr_set[16] = {false};
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (dev >= 0 && dev < 16 && !attr_set[dev]) {
+		cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+		    static_cast<int>(kSmemLimit));
+		if (e != cudaSuccess) return e;
+		attr_set[dev] = true;
+	}
+	CUtensorMap mapA, mapB;
+	TcParams p;
+	std::memcpy(&mapA, l.map_a, 128);
+	std::memcpy(&mapB, l.map_b, 128);
+	std::memcpy(&p, l.params, sizeof(p));
+	p.error_flag = error_flag;
+	conv_tc_kernel<<<l.grid, kThreads, l.smem_bytes, s>>>(mapA, mapB, p);
+	return cudaGetLastError();
+}
+
+}  // namespace ju

@@ -50,6 +50,28 @@ size_t conv_simt_weight_bytes(int ksize, int cin_padded, int cout);
 void conv_simt_pack_weights(const float *kernel, const float *scale, int ksize, int cin,
     int cin_padded, int cout, __half *dst);
 
+// ---- tcgen05 implicit-GEMM convolution (conv_tc.cu) ----------------------
+// A prepared launch: two TMA tensor maps (activations, weights) + parameters.
+// Built once per layer at plan time; replayed by the CUDA graph.
+struct ConvTcLaunch {
+	alignas(64) unsigned char map_a[128];
+	alignas(64) unsigned char map_b[128];
+	alignas(8) unsigned char params[192];
+	int grid;
+	unsigned int smem_bytes;
+};
+bool conv_tc_supported(const ConvArgs &a);
+// a.weights must point at DEVICE memory packed by conv_tc_pack_weights with
+// cin_padded == a.cin.  variant: bits 0-1 halo layout (0: one 18x10 box,
+// 1: one 18x16 box, 2: three 18x8 boxes), bit 2: descriptor base-offset mode.
+cudaError_t conv_tc_prepare(const ConvArgs &a, int variant, ConvTcLaunch *out);
+cudaError_t conv_tc_launch(const ConvTcLaunch &l, int *error_flag, cudaStream_t s);
+size_t conv_tc_weight_bytes(int ksize, int cin_padded, int cout);
+void conv_tc_pack_weights(const float *kernel, const float *scale, int ksize, int cin,
+    int cin_padded, int cout, __half *dst);
+void conv_tc_set_variant(int v);
+int conv_tc_get_variant();
+
 cudaError_t launch_maxpool2(const __half *in, __half *out, int batch, int h, int w, int c, cudaStream_t s);
 cudaError_t launch_upscale2(const __half *in, __half *out, int batch, int h, int w, int c, cudaStream_t s);
 

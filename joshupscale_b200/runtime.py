@@ -72,6 +72,8 @@ SYMBOLS = {
     "ju_launch_conv": (_I, [_I, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _I, _I,
                             _F, _I, _I, _VP]),
     "ju_pack_conv_weights": (C.c_int64, [_I, _VP, _VP, _I, _I, _I, _I, _VP]),
+    "ju_set_option": (_I, [C.c_char_p, _I]),
+    "ju_bench_conv": (_I, [_I, _I, _I, _I, _I, _I, _I, _I, _I, C.POINTER(C.c_double)]),
     "ju_launch_maxpool2": (_I, [_VP, _VP, _I, _I, _I, _I, _VP]),
     "ju_launch_upscale2": (_I, [_VP, _VP, _I, _I, _I, _I, _VP]),
     "ju_launch_warp_s2d": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
@@ -115,6 +117,19 @@ def load_library() -> C.CDLL:
 def _check(status: int) -> None:
     if status != 0:
         raise JoshUpscaleError(load_library().ju_last_error().decode(errors="replace"))
+
+
+def set_option(key: str, value: int) -> None:
+    _check(load_library().ju_set_option(key.encode(), int(value)))
+
+
+def bench_conv(impl: int, batch: int, h: int, w: int, cin: int, cout: int, ksize: int = 3,
+               residual: bool = False, iters: int = 20) -> float:
+    """Mean device time (usec) of one convolution launch on synthetic buffers."""
+    usec = C.c_double()
+    _check(load_library().ju_bench_conv(impl, batch, h, w, cin, cout, ksize, int(residual), iters,
+                                        C.byref(usec)))
+    return usec.value
 
 
 def device_count() -> int:

@@ -45,7 +45,7 @@ def test_recurrent_parity_small(tmp_path, preset, conditioned, nframes):
         m16, frac16, _ = u8_stats(got[t, ..., :3], emu[t, ..., :3])
         m32, _, psnr32 = u8_stats(got[t, ..., :3], ref[t, ..., :3])
         # against the fp16-emulating oracle only truncation flips remain
-        assert m16 <= 1 and frac16 < 0.02, (t, m16, frac16)
+        assert m16 <= 1 and frac16 < 0.06, (t, m16, frac16)
         assert m32 <= MAX_ABS_FP32 and psnr32 >= MIN_PSNR_DB, (t, m32, psnr32)
 
 
