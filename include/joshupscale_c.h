@@ -131,8 +131,8 @@ JU_API int ju_launch_conv(int impl, const void *in, const void *weights, const f
 JU_API int64_t ju_pack_conv_weights(int impl, const float *kernel, const float *scale,
     int ksize, int cin, int cin_padded, int cout, void *dst);
 
-/* Global integer options: "tc_variant" (tcgen05 conv halo/descriptor variant,
- * see conv_tc.cu; bits 0-1 halo layout, bit 2 base-offset mode). */
+/* Global integer options: "tc_variant" (tcgen05 conv halo layout, see
+ * conv_tc.cu: 0 = 18x10-pixel halo box, 1 = 18x16-pixel cross-check layout). */
 JU_API int ju_set_option(const char *key, int value);
 
 /* Stand-alone timing of one convolution shape: allocates its own buffers,

@@ -31,7 +31,7 @@ Engine::Engine(const ModelFile &model, int device, int batch)
 		JU_LOG_WARN << "device " << device << " is sm_" << prop.major << prop.minor
 		            << "; kernels are built for sm_100a only";
 	}
-	m_ConvImpl = envInt("JU_CONV_IMPL", 0);
+	m_ConvImpl = envInt("JU_CONV_IMPL", 1);  // 1 = tcgen05 (default), 0 = SIMT reference kernels
 	if (const char *v = std::getenv("JU_TC_VARIANT")) conv_tc_set_variant(std::atoi(v));
 	m_UseGraph = envInt("JU_NO_GRAPH", 0) == 0;
 	JU_CUDA(cudaStreamCreateWithFlags(&m_Stream, cudaStreamNonBlocking));

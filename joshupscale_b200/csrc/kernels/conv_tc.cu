@@ -346,8 +346,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 				uint32_t acc[32];
 				const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
 				                       static_cast<uint32_t>(as * p.nt + half * 32);
+				__syncwarp();  // tcgen05.ld is .sync.aligned: the warp must be converged
 				tmem_ld32(taddr, acc);
-				if (!valid) continue;
+				if (valid) {
 				const int co = t.n0 + half * 32;  // first of 32 consecutive output channels
 				size_t opix;
 				int oc;
@@ -416,7 +417,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 						op[c8] = o;
 					}
 				}
+				}  // valid
 			}
+			__syncwarp();
 			// all of this warp's TMEM reads are complete (wait::ld) -> release the stage
 			tcgen05_fence_before();
 			__syncwarp();
@@ -512,20 +515,21 @@ cudaError_t conv_tc_prepare(const ConvArgs &a, int variant, ConvTcLaunch *out) {
 	p.cout_stride = a.cout_stride;
 	const int taps = a.ksize * a.ksize;
 	const int halo_h = kTileH + a.ksize - 1;
-	const int pitch_mode = variant & 3;
-	p.base_off_mode = (variant >> 2) & 1;
+	// Halo layout.  Probed on B200 (profiles/r01_tc_probe_variants.json): the
+	// 128B swizzle XOR is a function of the absolute shared-memory address
+	// bits for both TMA and UMMA, so descriptor start addresses may be any
+	// multiple of 128 B inside a 1024B-aligned TMA tile, SBO need not be a
+	// multiple of 1024, and the descriptor base_offset field must stay 0
+	// (setting it to (addr>>7)&7 produces wrong results).  variant 1 keeps a
+	// 16-pixel pitch (SBO = 2048) as a cross-check layout.
+	p.base_off_mode = 0;
+	p.nbox = 1;
 	if (a.ksize == 1) {
 		p.pitch = kTileW;
-		p.nbox = 1;
-	} else if (pitch_mode == 0) {
-		p.pitch = kTileW + 2;
-		p.nbox = 1;
-	} else if (pitch_mode == 1) {
+	} else if ((variant & 3) == 1) {
 		p.pitch = 16;
-		p.nbox = 1;
 	} else {
-		p.pitch = kTileW;
-		p.nbox = 3;
+		p.pitch = kTileW + 2;
 	}
 	p.a_box_bytes = static_cast<uint32_t>(halo_h * p.pitch * 128);
 	p.a_region_bytes = (p.nbox * p.a_box_bytes + 1023u) & ~1023u;

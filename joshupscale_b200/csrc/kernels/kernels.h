@@ -62,8 +62,8 @@ struct ConvTcLaunch {
 };
 bool conv_tc_supported(const ConvArgs &a);
 // a.weights must point at DEVICE memory packed by conv_tc_pack_weights with
-// cin_padded == a.cin.  variant: bits 0-1 halo layout (0: one 18x10 box,
-// 1: one 18x16 box, 2: three 18x8 boxes), bit 2: descriptor base-offset mode.
+// cin_padded == a.cin.  variant: 0 = 18x10-pixel halo box (default),
+// 1 = 18x16-pixel halo box (cross-check layout).
 cudaError_t conv_tc_prepare(const ConvArgs &a, int variant, ConvTcLaunch *out);
 cudaError_t conv_tc_launch(const ConvTcLaunch &l, int *error_flag, cudaStream_t s);
 size_t conv_tc_weight_bytes(int ksize, int cin_padded, int cout);

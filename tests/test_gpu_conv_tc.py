@@ -1,0 +1,114 @@
+"""The tcgen05 implicit-GEMM convolution (conv_tc.cu) against the oracle and
+against the SIMT reference kernel, through the C-ABI (ju_launch_conv impl=1)."""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from joshupscale_b200 import kernels as jk
+from joshupscale_b200 import runtime as jrt
+from joshupscale_b200 import synthetic
+from oracle import reference_graph as og
+from tests.gpu_util import make_model, r16, require_gpu, u8_stats
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True, scope="module")
+def _gpu():
+    require_gpu()
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a, np.float32))
+
+
+TC_CASES = [
+    # b, h, w, cin, cout, ks  (tile = 16 rows x 8 cols: ragged edges, multi k-block, multi n-tile)
+    (1, 16, 8, 64, 64, 3), (1, 20, 13, 64, 64, 3), (2, 48, 40, 64, 64, 3), (1, 1, 1, 64, 64, 3),
+    (1, 17, 9, 51, 64, 3), (1, 16, 16, 128, 64, 3), (1, 32, 24, 64, 128, 3), (1, 16, 16, 12, 32, 3),
+    (1, 16, 24, 256, 256, 3), (1, 34, 60, 128, 256, 3), (1, 23, 31, 64, 32, 1), (1, 270, 480, 64, 64, 3),
+]
+
+
+@pytest.mark.parametrize("b,h,w,cin,cout,ks", TC_CASES)
+@pytest.mark.parametrize("mode", ["plain", "residual_relu", "lrelu_f32"])
+def test_conv_tc_vs_oracle(b, h, w, cin, cout, ks, mode):
+    rng = np.random.default_rng(cin * 1000 + cout + ks + h)
+    x = r16(rng.standard_normal((b, h, w, cin)) * 0.5)
+    k = (rng.standard_normal((ks, ks, cin, cout)) / np.sqrt(ks * ks * cin)).astype(np.float32)
+    scale = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    bias = rng.standard_normal(cout).astype(np.float32) * 0.1
+    res = r16(rng.standard_normal((b, h, w, cout)) * 0.5)
+    kw = dict(scale=scale, impl=jk.IMPL_TCGEN05)
+    want = og.conv2d_same(_t(x), og.r16(_t(k * scale))).numpy()
+    if mode == "residual_relu":
+        kw.update(bias=bias, residual=res, act=jk.ACT_RELU)
+        want = np.maximum(want + bias + res, 0)
+    elif mode == "lrelu_f32":
+        kw.update(bias=bias, act=jk.ACT_LRELU, slope=0.3, out_f32=True)
+        want = want + bias
+        want = np.where(want >= 0, want, want * np.float32(0.3))
+    got = jk.conv(x, k, **kw).astype(np.float32)
+    if mode != "lrelu_f32":
+        np.testing.assert_allclose(got, r16(want), rtol=2e-3, atol=1e-3)
+    else:
+        np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4)
+
+
+def test_conv_tc_equals_simt_kernel_closely():
+    """Two independent device implementations of the same layer."""
+    rng = np.random.default_rng(11)
+    x = r16(rng.standard_normal((1, 40, 56, 64)) * 0.5)
+    k = (rng.standard_normal((3, 3, 64, 64)) / 24).astype(np.float32)
+    a = jk.conv(x, k, act=jk.ACT_RELU, impl=jk.IMPL_SIMT).astype(np.float32)
+    b = jk.conv(x, k, act=jk.ACT_RELU, impl=jk.IMPL_TCGEN05).astype(np.float32)
+    np.testing.assert_allclose(a, b, rtol=2e-3, atol=1e-3)
+
+
+def test_conv_tc_transpose_shuffle():
+    rng = np.random.default_rng(5)
+    b, h, w, cin, cout = 1, 19, 14, 64, 32
+    x = r16(rng.standard_normal((b, h, w, cin)) * 0.5)
+    kt = (rng.standard_normal((2, 2, cout, cin)) / 8).astype(np.float32)
+    scale = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    bias = rng.standard_normal(cout).astype(np.float32) * 0.1
+    k1 = np.transpose(kt.reshape(4, cout, cin), (2, 0, 1)).reshape(1, 1, cin, 4 * cout)
+    got = jk.conv(x, k1, scale=np.tile(scale, 4), bias=np.tile(bias, 4), act=jk.ACT_RELU,
+                  shuffle2=True, impl=jk.IMPL_TCGEN05).astype(np.float32)
+    want = og.conv2d_transpose_k2s2(_t(x), og.r16(_t(kt * scale[None, None, :, None]))).numpy() + bias
+    np.testing.assert_allclose(got, r16(np.maximum(want, 0)), rtol=2e-3, atol=1e-3)
+
+
+def test_halo_layout_variants_agree():
+    rng = np.random.default_rng(12)
+    x = r16(rng.standard_normal((1, 33, 29, 64)) * 0.5)
+    k = (rng.standard_normal((3, 3, 64, 64)) / 24).astype(np.float32)
+    outs = []
+    for v in (0, 1):
+        jrt.set_option("tc_variant", v)
+        outs.append(jk.conv(x, k, impl=jk.IMPL_TCGEN05))
+    jrt.set_option("tc_variant", 0)
+    np.testing.assert_array_equal(outs[0].view(np.uint16), outs[1].view(np.uint16))
+
+
+def test_engine_runs_on_tensor_cores_and_matches_simt_engine(tmp_path):
+    """Whole graph with tcgen05 convs vs the whole graph with SIMT convs."""
+    cfg, w, path = make_model(tmp_path, "small")
+    frames = synthetic.frames(cfg.frame_height, cfg.frame_width, 5)
+    outs = {}
+    for impl in ("1", "0"):
+        os.environ["JU_CONV_IMPL"] = impl
+        try:
+            with jrt.Runtime(path) as rt:
+                assert rt.info.conv_impl == int(impl)
+                outs[impl] = np.stack([rt.process(f) for f in frames])
+        finally:
+            os.environ.pop("JU_CONV_IMPL", None)
+    m, frac, psnr = u8_stats(outs["1"], outs["0"])
+    assert m <= 1 and frac < 0.06 and psnr > 55
+    ref, _ = og.Graph(cfg, w, "fp32").run(frames)
+    m32, _, p32 = u8_stats(outs["1"][..., :3], ref[..., :3])
+    assert m32 <= 2 and p32 >= 45.0
