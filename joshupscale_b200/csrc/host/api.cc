@@ -362,6 +362,10 @@ int ju_set_option(const char *key, int value) {
 		if (!key) throw std::invalid_argument("null key");
 		if (std::strcmp(key, "tc_variant") == 0) {
 			ju::conv_tc_set_variant(value);
+		} else if (std::strcmp(key, "tc_tma_epilogue") == 0) {
+			ju::conv_tc_set_flags(value, -1);
+		} else if (std::strcmp(key, "tc_pdl") == 0) {
+			ju::conv_tc_set_flags(-1, value);
 		} else {
 			throw std::invalid_argument(std::string("unknown option ") + key);
 		}

@@ -33,6 +33,8 @@ Engine::Engine(const ModelFile &model, int device, int batch)
 	}
 	m_ConvImpl = envInt("JU_CONV_IMPL", 1);  // 1 = tcgen05 (default), 0 = SIMT reference kernels
 	if (const char *v = std::getenv("JU_TC_VARIANT")) conv_tc_set_variant(std::atoi(v));
+	if (const char *v = std::getenv("JU_TC_TMA_EPILOGUE")) conv_tc_set_flags(std::atoi(v), -1);
+	if (const char *v = std::getenv("JU_TC_PDL")) conv_tc_set_flags(-1, std::atoi(v));
 	m_UseGraph = envInt("JU_NO_GRAPH", 0) == 0;
 	JU_CUDA(cudaStreamCreateWithFlags(&m_Stream, cudaStreamNonBlocking));
 	try {

@@ -56,6 +56,8 @@ struct TcParams {
 	int base_off_mode;
 	int b_resident;
 	int stages;
+	int tma_epi;  // epilogue through shared memory: TMA residual load + TMA store
+	int pdl;      // launched with programmatic stream serialization
 	uint32_t a_box_bytes, a_region_bytes, stage_bytes, b_slice_bytes;
 	const float *bias;
 	const __half *residual;
@@ -123,6 +125,23 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
 	    " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
 	    "l"(map), "r"(bar), "r"(c0), "r"(c1)
 	    : "memory");
+}
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2,
+    int c3) {
+	asm volatile(
+	    "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+	    "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+	    : "memory");
+	asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+// the 4 epilogue warps only (threads 64..191)
+__device__ __forceinline__ void epilogue_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() {
+	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
 __device__ __forceinline__ void tcgen05_fence_before() {
@@ -202,6 +221,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams &p, int idx) {
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+    const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
     const TcParams p) {
 	extern __shared__ uint8_t smem_raw[];
 	// SWIZZLE_128B operands need 1024-byte aligned tiles
@@ -210,13 +230,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 	const uint32_t stages_bytes = static_cast<uint32_t>(p.stages) * p.stage_bytes;
 	const uint32_t resb_base = smem_base + stages_bytes;
 	const uint32_t resb_bytes = p.b_resident ? static_cast<uint32_t>(taps * p.kb) * p.b_slice_bytes : 0u;
-	const uint32_t bar_base = resb_base + resb_bytes;  // 8-byte aligned (all sizes are multiples of 1024)
+	// epilogue staging (tma_epi): 2 output tiles + 2 residual tiles of 128 px x 128 B, bias
+	constexpr uint32_t kEpiTile = 128u * 128u;
+	const uint32_t epi_out_base = resb_base + resb_bytes;
+	const uint32_t epi_res_base = epi_out_base + (p.tma_epi ? 2u * kEpiTile : 0u);
+	const uint32_t bias_base = epi_res_base + ((p.tma_epi && p.residual) ? 2u * kEpiTile : 0u);
+	const uint32_t bar_base = bias_base + 256u;  // 8-byte aligned (all sizes are multiples of 256)
 	auto full_bar = [&](int s) { return bar_base + 8u * s; };
 	auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
 	auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
 	auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 2 + s); };
 	const uint32_t w_bar = bar_base + 8u * (2 * kMaxStages + 4);
 	const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 5);
+	auto rfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 6 + s); };
+	auto rempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 8 + s); };
 
 	const int warp = threadIdx.x >> 5;
 	const int lane = threadIdx.x & 31;
@@ -230,6 +257,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 		for (int s = 0; s < 2; ++s) {
 			mbar_init(tfull_bar(s), 1);
 			mbar_init(tempty_bar(s), 4);  // one arrival per epilogue warp
+			mbar_init(rfull_bar(s), 1);
+			mbar_init(rempty_bar(s), 4);
 		}
 		mbar_init(w_bar, 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -247,8 +276,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
 	const int pad = (p.ks - 1) / 2;
-	const int halo_h = kTileH + p.ks - 1;
-	(void) halo_h;
+
+	// Programmatic dependent launch: everything above (barrier init, TMEM
+	// allocation) and the weight loads below do not depend on the previous
+	// kernel in the stream; activations are only touched after the wait.
+	if (p.pdl) grid_launch_dependents();
 
 	if (warp == 0) {
 		// ===================== TMA producer =====================
@@ -260,9 +292,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 					tma_load_2d(resb_base + s * p.b_slice_bytes, &map_b, w_bar, 0, s * p.cout);
 				}
 			}
-			int it = 0;
-			for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+			if (p.pdl) grid_dependency_wait();
+			int it = 0, tcount = 0;
+			for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
 				const TileCoord t = decode_tile(p, tile);
+				if (p.tma_epi && p.residual) {
+					const int rb = tcount & 1;
+					const uint32_t rph = (tcount >> 1) & 1;
+					mbar_wait(rempty_bar(rb), rph ^ 1u, p.error_flag, 6);
+					mbar_arrive_expect_tx(rfull_bar(rb), kEpiTile);
+					tma_load_4d(epi_res_base + rb * kEpiTile, &map_r, rfull_bar(rb), t.n0, t.x0, t.y0, t.b);
+				}
 				for (int kbi = 0; kbi < p.kb; ++kbi, ++it) {
 					const int s = it % p.stages;
 					const uint32_t ph = (it / p.stages) & 1;
@@ -333,11 +373,101 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 		const int q = warp & 3;  // TMEM lane quarter this warp may access
 		const int row = q * 32 + lane;
 		const int cpp = p.shuffle2 ? p.cout / 4 : p.cout;  // channels per output pixel
+		const int etid = threadIdx.x - 64;  // 0..127 within the epilogue warps
+		if (p.pdl) grid_dependency_wait();
 		int tcount = 0;
 		for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
 			const TileCoord t = decode_tile(p, tile);
 			const int as = tcount & 1;
 			const uint32_t aph = (tcount >> 1) & 1;
+			if (p.tma_epi) {
+				// ---- shared-memory epilogue: every global access is a TMA bulk copy ----
+				// thread `row` owns one pixel = one 128-byte row of the 128B-swizzled
+				// staging tiles: 16-byte chunk c of row r lives at r*128 + ((c ^ (r&7)) << 4)
+				if (etid < 64) {
+					const float bv = p.bias ? __ldg(p.bias + t.n0 + etid) : 0.f;
+					asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_base + 4u * etid), "f"(bv) : "memory");
+				}
+				if (etid == 0 && tcount >= 2) {
+					// the bulk store that read staging[as] two tiles ago must have drained
+					asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+				}
+				mbar_wait(tfull_bar(as), aph, p.error_flag, 5);
+				if (p.residual) mbar_wait(rfull_bar(as), aph, p.error_flag, 7);
+				tcgen05_fence_after();
+				epilogue_barrier();  // bias visible, staging[as] free
+				const uint32_t out_row = epi_out_base + as * kEpiTile + row * 128u;
+				const uint32_t res_row = epi_res_base + as * kEpiTile + row * 128u;
+				const uint32_t sw = static_cast<uint32_t>(row & 7);
+#pragma unroll
+				for (int half = 0; half < 2; ++half) {
+					uint32_t acc[32];
+					const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+					                       static_cast<uint32_t>(as * p.nt + half * 32);
+					__syncwarp();
+					tmem_ld32(taddr, acc);
+#pragma unroll
+					for (int c8 = 0; c8 < 4; ++c8) {
+						const int chunk = half * 4 + c8;  // 8 channels = 16 bytes of fp16
+						float v[8];
+#pragma unroll
+						for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(acc[c8 * 8 + e]);
+						float4 b0, b1;
+						asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+						             : "=f"(b0.x), "=f"(b0.y), "=f"(b0.z), "=f"(b0.w)
+						             : "r"(bias_base + 32u * chunk));
+						asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+						             : "=f"(b1.x), "=f"(b1.y), "=f"(b1.z), "=f"(b1.w)
+						             : "r"(bias_base + 32u * chunk + 16u));
+						v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+						v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+						const uint32_t off = (static_cast<uint32_t>(chunk) ^ sw) << 4;
+						if (p.residual) {
+							uint4 rv;
+							asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+							             : "=r"(rv.x), "=r"(rv.y), "=r"(rv.z), "=r"(rv.w)
+							             : "r"(res_row + off));
+							const __half2 *h2 = reinterpret_cast<const __half2 *>(&rv);
+#pragma unroll
+							for (int e = 0; e < 4; ++e) {
+								const float2 f = __half22float2(h2[e]);
+								v[e * 2] += f.x;
+								v[e * 2 + 1] += f.y;
+							}
+						}
+						if (p.act == ACT_RELU) {
+#pragma unroll
+							for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+						} else if (p.act == ACT_LRELU) {
+#pragma unroll
+							for (int e = 0; e < 8; ++e) v[e] = v[e] >= 0.f ? v[e] : v[e] * p.slope;
+						}
+						__half2 h0 = __floats2half2_rn(v[0], v[1]);
+						__half2 h1 = __floats2half2_rn(v[2], v[3]);
+						__half2 h2o = __floats2half2_rn(v[4], v[5]);
+						__half2 h3 = __floats2half2_rn(v[6], v[7]);
+						asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(out_row + off),
+						             "r"(*reinterpret_cast<uint32_t *>(&h0)), "r"(*reinterpret_cast<uint32_t *>(&h1)),
+						             "r"(*reinterpret_cast<uint32_t *>(&h2o)), "r"(*reinterpret_cast<uint32_t *>(&h3))
+						             : "memory");
+					}
+				}
+				// TMEM and residual tile consumed by this warp -> hand both back
+				tcgen05_fence_before();
+				__syncwarp();
+				if (lane == 0) {
+					mbar_arrive(tempty_bar(as));
+					if (p.residual) mbar_arrive(rempty_bar(as));
+				}
+				// make the generic-proxy smem writes visible to the TMA (async proxy)
+				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+				epilogue_barrier();
+				if (etid == 0) {
+					// out-of-range rows/columns of ragged tiles are clipped by the TMA store
+					tma_store_4d(&map_c, epi_out_base + as * kEpiTile, t.n0, t.x0, t.y0, t.b);
+				}
+				continue;
+			}
 			mbar_wait(tfull_bar(as), aph, p.error_flag, 5);
 			tcgen05_fence_after();
 			const int y = t.y0 + (row >> 3), x = t.x0 + (row & 7);
@@ -427,6 +557,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 		}
 	}
 
+	if (p.tma_epi && threadIdx.x == 64) {
+		asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+	}
 	tcgen05_fence_before();
 	__syncthreads();
 	if (warp == 1) {
@@ -457,10 +590,16 @@ EncodeTiledFn encodeTiled() {
 }
 
 int g_TcVariant = 0;
+int g_TcTmaEpi = 1;
+int g_TcPdl = 1;
 
 }  // namespace
 
 void conv_tc_set_variant(int v) { g_TcVariant = v; }
+void conv_tc_set_flags(int tma_epilogue, int pdl) {
+	if (tma_epilogue >= 0) g_TcTmaEpi = tma_epilogue;
+	if (pdl >= 0) g_TcPdl = pdl;
+}
 int conv_tc_get_variant() { return g_TcVariant; }
 
 bool conv_tc_supported(const ConvArgs &a) {
@@ -537,10 +676,15 @@ cudaError_t conv_tc_prepare(const ConvArgs &a, int variant, ConvTcLaunch *out) {
 	const uint32_t all_b = static_cast<uint32_t>(taps * p.kb) * p.b_slice_bytes;
 	p.b_resident = (p.n_tiles == 1 && all_b <= 96 * 1024) ? 1 : 0;
 	p.stage_bytes = p.a_region_bytes + (p.b_resident ? 0u : taps * p.b_slice_bytes);
-	const uint32_t fixed = 1024u + 256u + (p.b_resident ? all_b : 0u);
+	// shared-memory epilogue (TMA residual load + TMA store) for the common
+	// fp16, 64-channel-tile, non-shuffled case
+	p.tma_epi = (!a.out_f32 && !a.shuffle2 && p.nt == 64 && a.cout_stride % 8 == 0 && g_TcTmaEpi) ? 1 : 0;
+	p.pdl = g_TcPdl ? 1 : 0;
+	const uint32_t epi_bytes = p.tma_epi ? (a.residual ? 4u : 2u) * 128u * 128u : 0u;
+	const uint32_t fixed = 1024u + 512u + (p.b_resident ? all_b : 0u) + epi_bytes;
+	if (fixed + 2 * p.stage_bytes > kSmemLimit) return cudaErrorInvalidValue;
 	int stages = static_cast<int>((kSmemLimit - fixed) / p.stage_bytes);
 	if (stages > kMaxStages) stages = kMaxStages;
-	if (stages < 2) return cudaErrorInvalidValue;
 	p.stages = stages;
 	p.bias = a.bias;
 	p.residual = a.residual;
@@ -551,7 +695,29 @@ cudaError_t conv_tc_prepare(const ConvArgs &a, int variant, ConvTcLaunch *out) {
 	p.shuffle2 = a.shuffle2;
 	p.error_flag = nullptr;
 
-	CUtensorMap mapA, mapB;
+	CUtensorMap mapA, mapB, mapC, mapR;
+	std::memset(&mapC, 0, sizeof(mapC));
+	std::memset(&mapR, 0, sizeof(mapR));
+	if (p.tma_epi) {
+		// output / residual tensors [batch, h, w, cout_stride] fp16, one 16x8-pixel x 64-channel tile per copy
+		cuuint64_t dims[4] = {static_cast<cuuint64_t>(a.cout_stride), static_cast<cuuint64_t>(a.w),
+		    static_cast<cuuint64_t>(a.h), static_cast<cuuint64_t>(a.batch)};
+		cuuint64_t strides[3] = {static_cast<cuuint64_t>(a.cout_stride) * 2,
+		    static_cast<cuuint64_t>(a.w) * a.cout_stride * 2,
+		    static_cast<cuuint64_t>(a.h) * a.w * a.cout_stride * 2};
+		cuuint32_t box[4] = {64, kTileW, kTileH, 1};
+		cuuint32_t estr[4] = {1, 1, 1, 1};
+		CUresult r = encode(&mapC, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, a.out, dims, strides, box, estr,
+		    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+		    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+		if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+		if (a.residual) {
+			r = encode(&mapR, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half *>(a.residual), dims, strides,
+			    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+			    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+			if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+		}
+	}
 	{
 		cuuint64_t dims[4] = {static_cast<cuuint64_t>(a.cin_stride), static_cast<cuuint64_t>(a.w),
 		    static_cast<cuuint64_t>(a.h), static_cast<cuuint64_t>(a.batch)};
@@ -577,12 +743,15 @@ cudaError_t conv_tc_prepare(const ConvArgs &a, int variant, ConvTcLaunch *out) {
 	}
 	std::memcpy(out->map_a, &mapA, 128);
 	std::memcpy(out->map_b, &mapB, 128);
+	std::memcpy(out->map_c, &mapC, 128);
+	std::memcpy(out->map_r, &mapR, 128);
 	std::memcpy(out->params, &p, sizeof(p));
 	int dev = 0, sms = 148;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 	out->grid = p.total_tiles < sms ? p.total_tiles : sms;
-	out->smem_bytes = 1024u + static_cast<uint32_t>(p.stages) * p.stage_bytes + (p.b_resident ? all_b : 0u) + 256u;
+	out->smem_bytes = fixed + static_cast<uint32_t>(p.stages) * p.stage_bytes;
+	out->pdl = p.pdl;
 	return cudaSuccess;
 }
 
@@ -596,14 +765,25 @@ cudaError_t conv_tc_launch(const ConvTcLaunch &l, int *error_flag, cudaStream_t 
 		if (e != cudaSuccess) return e;
 		attr_set[dev] = true;
 	}
-	CUtensorMap mapA, mapB;
+	CUtensorMap mapA, mapB, mapC, mapR;
 	TcParams p;
 	std::memcpy(&mapA, l.map_a, 128);
 	std::memcpy(&mapB, l.map_b, 128);
+	std::memcpy(&mapC, l.map_c, 128);
+	std::memcpy(&mapR, l.map_r, 128);
 	std::memcpy(&p, l.params, sizeof(p));
 	p.error_flag = error_flag;
-	conv_tc_kernel<<<l.grid, kThreads, l.smem_bytes, s>>>(mapA, mapB, p);
-	return cudaGetLastError();
+	cudaLaunchConfig_t cfg{};
+	cfg.gridDim = dim3(l.grid);
+	cfg.blockDim = dim3(kThreads);
+	cfg.dynamicSmemBytes = l.smem_bytes;
+	cfg.stream = s;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = l.pdl ? 1 : 0;
+	return cudaLaunchKernelEx(&cfg, conv_tc_kernel, mapA, mapB, mapC, mapR, p);
 }
 
 }  // namespace ju

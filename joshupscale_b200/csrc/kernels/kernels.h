@@ -56,9 +56,12 @@ void conv_simt_pack_weights(const float *kernel, const float *scale, int ksize, 
 struct ConvTcLaunch {
 	alignas(64) unsigned char map_a[128];
 	alignas(64) unsigned char map_b[128];
+	alignas(64) unsigned char map_c[128];  // output (TMA store)
+	alignas(64) unsigned char map_r[128];  // residual (TMA load)
 	alignas(8) unsigned char params[192];
 	int grid;
 	unsigned int smem_bytes;
+	int pdl;
 };
 bool conv_tc_supported(const ConvArgs &a);
 // a.weights must point at DEVICE memory packed by conv_tc_pack_weights with
@@ -70,6 +73,9 @@ size_t conv_tc_weight_bytes(int ksize, int cin_padded, int cout);
 void conv_tc_pack_weights(const float *kernel, const float *scale, int ksize, int cin,
     int cin_padded, int cout, __half *dst);
 void conv_tc_set_variant(int v);
+// -1 keeps the current value.  tma_epilogue: shared-memory epilogue with TMA
+// residual load + TMA store; pdl: programmatic dependent launch.
+void conv_tc_set_flags(int tma_epilogue, int pdl);
 int conv_tc_get_variant();
 
 cudaError_t launch_maxpool2(const __half *in, __half *out, int batch, int h, int w, int c, cudaStream_t s);
