@@ -27,13 +27,15 @@ CASES = [
 ]
 
 
-def child(variant: int):
+def child(variant: int, epi: int = 1, pdl: int = 1):
     import numpy as np
     import torch
     from joshupscale_b200 import kernels as jk
     from joshupscale_b200 import runtime as jrt
     from oracle import reference_graph as og
     jrt.set_option("tc_variant", variant)
+    jrt.set_option("tc_tma_epilogue", epi)
+    jrt.set_option("tc_pdl", pdl)
     results = []
     for (b, h, w, cin, cout, ks, mode) in CASES:
         rng = np.random.default_rng(cin + cout + h)
@@ -83,15 +85,16 @@ def child(variant: int):
 
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "--child":
-        child(int(sys.argv[2]))
+        child(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))
         return
     out = {}
-    for v in (2, 0, 4, 1, 5):
-        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", str(v)],
+    for v, epi, pdl in ((0, 0, 0), (0, 1, 0), (0, 1, 1), (0, 0, 1), (1, 1, 1)):
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", str(v), str(epi), str(pdl)],
                            capture_output=True, text=True, timeout=300)
         lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
-        out[str(v)] = dict(rc=r.returncode, lines=lines, stderr=r.stderr[-600:])
-        print("variant", v, "rc", r.returncode, [l.get("ok", l) for l in lines], flush=True)
+        key = f"variant{v}_epi{epi}_pdl{pdl}"
+        out[key] = dict(rc=r.returncode, lines=lines, stderr=r.stderr[-600:])
+        print(key, "rc", r.returncode, [l.get("ok", l) for l in lines], r.stderr[-300:], flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "tc_probe.json"), "w"), indent=1)
 

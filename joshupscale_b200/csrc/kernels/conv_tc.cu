@@ -219,6 +219,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams &p, int idx) {
 	return t;
 }
 
+template <int KS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
     const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
@@ -226,7 +227,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 	extern __shared__ uint8_t smem_raw[];
 	// SWIZZLE_128B operands need 1024-byte aligned tiles
 	const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-	const int taps = p.ks * p.ks;
+	constexpr int taps = KS * KS;
 	const uint32_t stages_bytes = static_cast<uint32_t>(p.stages) * p.stage_bytes;
 	const uint32_t resb_base = smem_base + stages_bytes;
 	const uint32_t resb_bytes = p.b_resident ? static_cast<uint32_t>(taps * p.kb) * p.b_slice_bytes : 0u;
@@ -275,7 +276,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 	uint32_t tmem_base;
 	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
-	const int pad = (p.ks - 1) / 2;
+	constexpr int pad = (KS - 1) / 2;
 
 	// Programmatic dependent launch: everything above (barrier init, TMEM
 	// allocation) and the weight loads below do not depend on the previous
@@ -308,12 +309,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 					const uint32_t ph = (it / p.stages) & 1;
 					mbar_wait(empty_bar(s), ph ^ 1u, p.error_flag, 1);
 					const uint32_t stage = smem_base + s * p.stage_bytes;
-					const uint32_t bytes = p.nbox * p.a_box_bytes + (p.b_resident ? 0u : taps * p.b_slice_bytes);
+					const uint32_t bytes = p.a_box_bytes + (p.b_resident ? 0u : taps * p.b_slice_bytes);
 					mbar_arrive_expect_tx(full_bar(s), bytes);
-					for (int bx = 0; bx < p.nbox; ++bx) {
-						tma_load_4d(stage + bx * p.a_box_bytes, &map_a, full_bar(s), kbi * 64,
-						    t.x0 - pad + (p.nbox == 3 ? bx : 0), t.y0 - pad, t.b);
-					}
+					tma_load_4d(stage, &map_a, full_bar(s), kbi * 64, t.x0 - pad, t.y0 - pad, t.b);
 					if (!p.b_resident) {
 						for (int tap = 0; tap < taps; ++tap) {
 							tma_load_2d(stage + p.a_region_bytes + tap * p.b_slice_bytes, &map_b, full_bar(s), 0,
@@ -325,9 +323,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 		}
 	} else if (warp == 1) {
 		// ===================== MMA issuer =====================
+		// One thread issues every tcgen05.mma of the CTA, so its instruction
+		// stream is the critical path: descriptors are split into a constant high
+		// word and a 32-bit low word (start address >> 4) that only needs one add
+		// per MMA; tap / k offsets are compile-time constants after unrolling.
 		if (lane == 0) {
 			const uint32_t idesc = make_idesc(p.nt);
 			const uint32_t a_sbo = static_cast<uint32_t>(p.pitch) * 128u;
+			const uint32_t a_hi = static_cast<uint32_t>(make_smem_desc(0, a_sbo, 0) >> 32);
+			const uint32_t b_hi = static_cast<uint32_t>(make_smem_desc(0, 1024u, 0) >> 32);
+			const uint32_t lo_flags = 1u << 16;            // LBO field (unused for swizzled K-major)
+			const uint32_t row_off = static_cast<uint32_t>(p.pitch) * 8u;  // one halo row, in 16-byte units
+			const uint32_t b_slice16 = p.b_slice_bytes >> 4;
 			if (p.b_resident) {
 				mbar_wait(w_bar, 0, p.error_flag, 2);
 			}
@@ -344,23 +351,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 					mbar_wait(full_bar(s), ph, p.error_flag, 4);
 					tcgen05_fence_after();
 					const uint32_t stage = smem_base + s * p.stage_bytes;
+					const uint32_t a_lo = lo_flags | (stage >> 4);
+					const uint32_t b_lo = lo_flags | ((p.b_resident ? resb_base + kbi * p.b_slice_bytes
+					                                               : stage + p.a_region_bytes) >> 4);
+					const uint32_t b_tap16 = p.b_resident ? b_slice16 * p.kb : b_slice16;
+					uint32_t first = kbi == 0 ? 0u : 1u;
+#pragma unroll
 					for (int tap = 0; tap < taps; ++tap) {
-						const int dy = tap / p.ks, dx = tap % p.ks;
-						uint32_t a_addr;
-						if (p.nbox == 3) {
-							a_addr = stage + dx * p.a_box_bytes + dy * p.pitch * 128;
-						} else {
-							a_addr = stage + (dy * p.pitch + dx) * 128;
-						}
-						const uint32_t b_addr = p.b_resident
-						                            ? resb_base + (tap * p.kb + kbi) * p.b_slice_bytes
-						                            : stage + p.a_region_bytes + tap * p.b_slice_bytes;
-						const uint32_t boff = p.base_off_mode ? ((a_addr >> 7) & 7u) : 0u;
+						const uint32_t a_tap = a_lo + (tap / KS) * row_off + (tap % KS) * 8u;
+						const uint32_t b_tap = b_lo + tap * b_tap16;
 #pragma unroll
 						for (int k16 = 0; k16 < 4; ++k16) {
-							const uint64_t a_desc = make_smem_desc(a_addr + k16 * 32, a_sbo, boff);
-							const uint64_t b_desc = make_smem_desc(b_addr + k16 * 32, 1024u, 0u);
-							umma_f16(d_tmem, a_desc, b_desc, idesc, (kbi | tap | k16) != 0 ? 1u : 0u);
+							const uint64_t a_desc = (static_cast<uint64_t>(a_hi) << 32) | (a_tap + k16 * 2u);
+							const uint64_t b_desc = (static_cast<uint64_t>(b_hi) << 32) | (b_tap + k16 * 2u);
+							umma_f16(d_tmem, a_desc, b_desc, idesc, (tap | k16) != 0 ? 1u : first);
 						}
 					}
 					umma_commit(empty_bar(s));  // frees the stage when these MMAs have read it
@@ -760,7 +764,10 @@ cudaError_t conv_tc_launch(const ConvTcLaunch &l, int *error_flag, cudaStream_t 
 	int dev = 0;
 	cudaGetDevice(&dev);
 	if (dev >= 0 && dev < 16 && !attr_set[dev]) {
-		cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+		cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+		    static_cast<int>(kSmemLimit));
+		if (e != cudaSuccess) return e;
+		e = cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 		    static_cast<int>(kSmemLimit));
 		if (e != cudaSuccess) return e;
 		attr_set[dev] = true;
@@ -783,7 +790,8 @@ cudaError_t conv_tc_launch(const ConvTcLaunch &l, int *error_flag, cudaStream_t 
 	attr[0].val.programmaticStreamSerializationAllowed = 1;
 	cfg.attrs = attr;
 	cfg.numAttrs = l.pdl ? 1 : 0;
-	return cudaLaunchKernelEx(&cfg, conv_tc_kernel, mapA, mapB, mapC, mapR, p);
+	if (p.ks == 3) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<3>, mapA, mapB, mapC, mapR, p);
+	return cudaLaunchKernelEx(&cfg, conv_tc_kernel<1>, mapA, mapB, mapC, mapR, p);
 }
 
 }  // namespace ju
