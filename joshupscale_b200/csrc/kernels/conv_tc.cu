@@ -684,8 +684,14 @@ cudaError_t conv_tc_prepare(const ConvArgs &a, int variant, ConvTcLaunch *out) {
 	// fp16, 64-channel-tile, non-shuffled case
 	p.tma_epi = (!a.out_f32 && !a.shuffle2 && p.nt == 64 && a.cout_stride % 8 == 0 && g_TcTmaEpi) ? 1 : 0;
 	p.pdl = g_TcPdl ? 1 : 0;
-	const uint32_t epi_bytes = p.tma_epi ? (a.residual ? 4u : 2u) * 128u * 128u : 0u;
-	const uint32_t fixed = 1024u + 512u + (p.b_resident ? all_b : 0u) + epi_bytes;
+	uint32_t epi_bytes = p.tma_epi ? (a.residual ? 4u : 2u) * 128u * 128u : 0u;
+	uint32_t fixed = 1024u + 512u + (p.b_resident ? all_b : 0u) + epi_bytes;
+	if (fixed + 2 * p.stage_bytes > kSmemLimit) {
+		// streamed-weight layers with big stages: fall back to the register epilogue
+		p.tma_epi = 0;
+		epi_bytes = 0;
+		fixed = 1024u + 512u + (p.b_resident ? all_b : 0u);
+	}
 	if (fixed + 2 * p.stage_bytes > kSmemLimit) return cudaErrorInvalidValue;
 	int stages = static_cast<int>((kSmemLimit - fixed) / p.stage_bytes);
 	if (stages > kMaxStages) stages = kMaxStages;
