@@ -198,8 +198,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 	      "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
 	    : "r"(taddr)
 	    : "memory");
-	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 struct TileCoord {
 	int b, y0, x0, n0;
@@ -294,16 +295,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 				}
 			}
 			if (p.pdl) grid_dependency_wait();
-			int it = 0, tcount = 0;
+			// The residual tile of tile i is consumed by the epilogue one tile after
+			// the MMAs of tile i start, so it is requested after the halo of tile
+			// i+1: the halo ring never waits behind the (shallower) residual ring.
+			auto load_residual = [&](int tc, int tile) {
+				const TileCoord t = decode_tile(p, tile);
+				const int rb = tc & 1;
+				const uint32_t rph = (tc >> 1) & 1;
+				mbar_wait(rempty_bar(rb), rph ^ 1u, p.error_flag, 6);
+				mbar_arrive_expect_tx(rfull_bar(rb), kEpiTile);
+				tma_load_4d(epi_res_base + rb * kEpiTile, &map_r, rfull_bar(rb), t.n0, t.x0, t.y0, t.b);
+			};
+			const bool with_res = p.tma_epi && p.residual;
+			int it = 0, tcount = 0, prev_tile = -1;
 			for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
 				const TileCoord t = decode_tile(p, tile);
-				if (p.tma_epi && p.residual) {
-					const int rb = tcount & 1;
-					const uint32_t rph = (tcount >> 1) & 1;
-					mbar_wait(rempty_bar(rb), rph ^ 1u, p.error_flag, 6);
-					mbar_arrive_expect_tx(rfull_bar(rb), kEpiTile);
-					tma_load_4d(epi_res_base + rb * kEpiTile, &map_r, rfull_bar(rb), t.n0, t.x0, t.y0, t.b);
-				}
 				for (int kbi = 0; kbi < p.kb; ++kbi, ++it) {
 					const int s = it % p.stages;
 					const uint32_t ph = (it / p.stages) & 1;
@@ -319,7 +325,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 						}
 					}
 				}
+				if (with_res && prev_tile >= 0) load_residual(tcount - 1, prev_tile);
+				prev_tile = tile;
 			}
+			if (with_res && prev_tile >= 0) load_residual(tcount - 1, prev_tile);
 		}
 	} else if (warp == 1) {
 		// ===================== MMA issuer =====================
@@ -378,6 +387,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 		const int row = q * 32 + lane;
 		const int cpp = p.shuffle2 ? p.cout / 4 : p.cout;  // channels per output pixel
 		const int etid = threadIdx.x - 64;  // 0..127 within the epilogue warps
+		uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic pointer to the aligned base
+		float bias_reg[64];
 		if (p.pdl) grid_dependency_wait();
 		int tcount = 0;
 		for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
@@ -387,81 +398,79 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 			if (p.tma_epi) {
 				// ---- shared-memory epilogue: every global access is a TMA bulk copy ----
 				// thread `row` owns one pixel = one 128-byte row of the 128B-swizzled
-				// staging tiles: 16-byte chunk c of row r lives at r*128 + ((c ^ (r&7)) << 4)
-				if (etid < 64) {
-					const float bv = p.bias ? __ldg(p.bias + t.n0 + etid) : 0.f;
-					asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_base + 4u * etid), "f"(bv) : "memory");
+				// staging tiles: 16-byte chunk c of row r lives at r*128 + ((c ^ (r&7)) << 4).
+				// One epilogue warp per SM sub-partition, so latency must be hidden by ILP
+				// inside the thread: bias stays in registers across tiles, the residual
+				// row and both accumulator halves are fetched up-front.
+				if (tcount == 0 || p.n_tiles > 1) {
+#pragma unroll
+					for (int c = 0; c < 64; ++c) bias_reg[c] = p.bias ? __ldg(p.bias + t.n0 + c) : 0.f;
 				}
 				if (etid == 0 && tcount >= 2) {
 					// the bulk store that read staging[as] two tiles ago must have drained
 					asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
 				}
-				mbar_wait(tfull_bar(as), aph, p.error_flag, 5);
-				if (p.residual) mbar_wait(rfull_bar(as), aph, p.error_flag, 7);
-				tcgen05_fence_after();
-				epilogue_barrier();  // bias visible, staging[as] free
-				const uint32_t out_row = epi_out_base + as * kEpiTile + row * 128u;
-				const uint32_t res_row = epi_res_base + as * kEpiTile + row * 128u;
 				const uint32_t sw = static_cast<uint32_t>(row & 7);
+				uint4 res[8];
+				if (p.residual) {
+					mbar_wait(rfull_bar(as), aph, p.error_flag, 7);
+					const uint4 *res_row = reinterpret_cast<const uint4 *>(
+					    smem_gen + (epi_res_base - smem_base) + as * kEpiTile + row * 128u);
 #pragma unroll
-				for (int half = 0; half < 2; ++half) {
-					uint32_t acc[32];
-					const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-					                       static_cast<uint32_t>(as * p.nt + half * 32);
-					__syncwarp();
-					tmem_ld32(taddr, acc);
-#pragma unroll
-					for (int c8 = 0; c8 < 4; ++c8) {
-						const int chunk = half * 4 + c8;  // 8 channels = 16 bytes of fp16
-						float v[8];
-#pragma unroll
-						for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(acc[c8 * 8 + e]);
-						float4 b0, b1;
-						asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-						             : "=f"(b0.x), "=f"(b0.y), "=f"(b0.z), "=f"(b0.w)
-						             : "r"(bias_base + 32u * chunk));
-						asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-						             : "=f"(b1.x), "=f"(b1.y), "=f"(b1.z), "=f"(b1.w)
-						             : "r"(bias_base + 32u * chunk + 16u));
-						v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-						v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-						const uint32_t off = (static_cast<uint32_t>(chunk) ^ sw) << 4;
-						if (p.residual) {
-							uint4 rv;
-							asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-							             : "=r"(rv.x), "=r"(rv.y), "=r"(rv.z), "=r"(rv.w)
-							             : "r"(res_row + off));
-							const __half2 *h2 = reinterpret_cast<const __half2 *>(&rv);
-#pragma unroll
-							for (int e = 0; e < 4; ++e) {
-								const float2 f = __half22float2(h2[e]);
-								v[e * 2] += f.x;
-								v[e * 2 + 1] += f.y;
-							}
-						}
-						if (p.act == ACT_RELU) {
-#pragma unroll
-							for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
-						} else if (p.act == ACT_LRELU) {
-#pragma unroll
-							for (int e = 0; e < 8; ++e) v[e] = v[e] >= 0.f ? v[e] : v[e] * p.slope;
-						}
-						__half2 h0 = __floats2half2_rn(v[0], v[1]);
-						__half2 h1 = __floats2half2_rn(v[2], v[3]);
-						__half2 h2o = __floats2half2_rn(v[4], v[5]);
-						__half2 h3 = __floats2half2_rn(v[6], v[7]);
-						asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(out_row + off),
-						             "r"(*reinterpret_cast<uint32_t *>(&h0)), "r"(*reinterpret_cast<uint32_t *>(&h1)),
-						             "r"(*reinterpret_cast<uint32_t *>(&h2o)), "r"(*reinterpret_cast<uint32_t *>(&h3))
-						             : "memory");
-					}
+					for (int c = 0; c < 8; ++c) res[c] = res_row[c ^ sw];
 				}
-				// TMEM and residual tile consumed by this warp -> hand both back
+				mbar_wait(tfull_bar(as), aph, p.error_flag, 5);
+				tcgen05_fence_after();
+				uint32_t acc0[32], acc1[32];
+				const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+				                       static_cast<uint32_t>(as * p.nt);
+				__syncwarp();
+				tmem_ld32(taddr, acc0);
+				tmem_ld32(taddr + 32, acc1);
+				tmem_ld_wait();
+				// TMEM and residual tile are in registers -> hand both back early
 				tcgen05_fence_before();
 				__syncwarp();
 				if (lane == 0) {
 					mbar_arrive(tempty_bar(as));
 					if (p.residual) mbar_arrive(rempty_bar(as));
+				}
+				epilogue_barrier();  // staging[as] free (wait_group.read above)
+				uint4 *out_row = reinterpret_cast<uint4 *>(
+				    smem_gen + (epi_out_base - smem_base) + as * kEpiTile + row * 128u);
+#pragma unroll
+				for (int c = 0; c < 8; ++c) {
+					float v[8];
+#pragma unroll
+					for (int e = 0; e < 8; ++e) {
+						v[e] = __uint_as_float(c < 4 ? acc0[c * 8 + e] : acc1[(c - 4) * 8 + e]) + bias_reg[c * 8 + e];
+					}
+					if (p.residual) {
+						const __half2 *h2 = reinterpret_cast<const __half2 *>(&res[c]);
+#pragma unroll
+						for (int e = 0; e < 4; ++e) {
+							const float2 f = __half22float2(h2[e]);
+							v[e * 2] += f.x;
+							v[e * 2 + 1] += f.y;
+						}
+					}
+					if (p.act == ACT_RELU) {
+#pragma unroll
+						for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+					} else if (p.act == ACT_LRELU) {
+#pragma unroll
+						for (int e = 0; e < 8; ++e) v[e] = v[e] >= 0.f ? v[e] : v[e] * p.slope;
+					}
+					uint4 o;
+					__half2 h0 = __floats2half2_rn(v[0], v[1]);
+					__half2 h1 = __floats2half2_rn(v[2], v[3]);
+					__half2 h2o = __floats2half2_rn(v[4], v[5]);
+					__half2 h3 = __floats2half2_rn(v[6], v[7]);
+					o.x = *reinterpret_cast<uint32_t *>(&h0);
+					o.y = *reinterpret_cast<uint32_t *>(&h1);
+					o.z = *reinterpret_cast<uint32_t *>(&h2o);
+					o.w = *reinterpret_cast<uint32_t *>(&h3);
+					out_row[c ^ sw] = o;
 				}
 				// make the generic-proxy smem writes visible to the TMA (async proxy)
 				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -482,6 +491,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 				                       static_cast<uint32_t>(as * p.nt + half * 32);
 				__syncwarp();  // tcgen05.ld is .sync.aligned: the warp must be converged
 				tmem_ld32(taddr, acc);
+				tmem_ld_wait();
 				if (valid) {
 				const int co = t.n0 + half * 32;  // first of 32 consecutive output channels
 				size_t opix;
