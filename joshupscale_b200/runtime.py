@@ -235,7 +235,7 @@ class Runtime:
         ops = (JuOpTime * count.value)()
         _check(self._lib.ju_profile_ops(self._h, iters, ops, count.value, C.byref(count)))
         return [dict(name=o.name.decode(), usec=o.usec, flops=o.flops, bytes=o.bytes,
-                     tensor_bound=bool(o.tensor_bound)) for o in ops]
+                     tensor_bound=bool(o.tensor_bound), launches=o.reserved) for o in ops]
 
 
 class Session:
