@@ -164,6 +164,16 @@ JU_API int ju_launch_warp_s2d(const void *pre_gen, const float *flow_head, const
 JU_API int ju_launch_final(const void *mid, const float *w2, const float *bias2, const uint8_t *frames,
     uint8_t *out_bgrx, void *pre_gen_next, float *out_raw, int batch, int h, int w, void *stream);
 
+/* Fused generator tail (tcgen05): conv_trans_1 (+folded BN, activation) ->
+ * conv_trans_2 + bias -> tanh -> + legacy-bilinear x4 of the input -> clip ->
+ * BGRX u8 + fp16 state, without materialising the [2H,2W,32] intermediate
+ * (models.py:559-593, 808-823).  trunk: [batch,H,W,64] fp16.  w1: conv_trans_1
+ * expressed as a 1x1 conv (1,1,64,128) with channel (i*2+j)*32+o, packed by
+ * ju_pack_conv_weights(impl=1); bias1[128].  Other arguments as ju_launch_final. */
+JU_API int ju_launch_tail(const void *trunk, const void *w1, const float *bias1, const float *w2,
+    const float *bias2, const uint8_t *frames, uint8_t *out_bgrx, void *pre_gen_next, float *out_raw,
+    int batch, int h, int w, int act, float slope, void *stream);
+
 /* raw device memory helpers for the ctypes-side tests (no torch needed) */
 JU_API int ju_dev_alloc(void **ptr, uint64_t bytes);
 JU_API int ju_dev_free(void *ptr);

@@ -480,6 +480,36 @@ int ju_launch_final(const void *mid, const float *w2, const float *bias2, const 
 	});
 }
 
+int ju_launch_tail(const void *trunk, const void *w1, const float *bias1, const float *w2, const float *bias2,
+    const uint8_t *frames, uint8_t *out_bgrx, void *pre_gen_next, float *out_raw, int batch, int h, int w,
+    int act, float slope, void *stream) {
+	return guarded([&] {
+		requireDevice();
+		TempIo io(frames, out_bgrx, batch, h, w);
+		auto s = static_cast<cudaStream_t>(stream);
+		ju::TailArgs a{};
+		a.in = static_cast<const __half *>(trunk);
+		a.cin_stride = 64;
+		a.weights1 = w1;
+		a.bias1 = bias1;
+		a.w2 = w2;
+		a.bias2 = bias2;
+		a.io = io.get();
+		a.pre_gen_next = static_cast<__half *>(pre_gen_next);
+		a.out_raw = out_raw;
+		a.batch = batch;
+		a.h = h;
+		a.w = w;
+		a.act = act;
+		a.slope = slope;
+		a.pdl = 0;
+		ju::TailTcLaunch l;
+		JU_CUDA(ju::tail_tc_prepare(a, &l));
+		JU_CUDA(ju::tail_tc_launch(l, nullptr, s));
+		JU_CUDA(cudaStreamSynchronize(s));
+	});
+}
+
 // ---- raw device helpers ---------------------------------------------------
 
 int ju_dev_alloc(void **ptr, uint64_t bytes) {

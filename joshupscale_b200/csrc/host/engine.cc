@@ -385,7 +385,42 @@ void Engine::buildPlan(int parity) {
 		        static_cast<std::uint64_t>(gs)},
 		    m_Trunk[0].bytes(), false);
 	}
-	plan.push_back(convOp(layer("generator/conv_trans_1"), cur, gs, nullptr, m_Mid.get(), 32, H, W, false));
+	ConvLayer *ct1 = layer("generator/conv_trans_1");
+	const bool fusedTail = m_ConvImpl == 1 && ct1->wTc.get() && gs % 64 == 0 && s.genFilters == 64 &&
+	                       envInt("JU_FUSED_TAIL", 1) != 0;
+	if (fusedTail) {
+		// conv_trans_1 + conv_trans_2 + tanh + upscale + add + clip + pack + state in ONE kernel
+		TailArgs ta{};
+		ta.in = cur;
+		ta.cin_stride = gs;
+		ta.weights1 = ct1->wTc.get();
+		ta.bias1 = ct1->bias.as<float>();
+		ta.w2 = m_W2.as<float>();
+		ta.bias2 = m_B2.as<float>();
+		ta.io = io;
+		ta.pre_gen_next = preGenNext;
+		ta.out_raw = nullptr;
+		ta.batch = B;
+		ta.h = H;
+		ta.w = W;
+		ta.act = ct1->act;
+		ta.slope = ct1->slope;
+		ta.pdl = 1;
+		TailTcLaunch launch;
+		checkCuda(tail_tc_prepare(ta, &launch), "tail_tc_prepare");
+		Op op;
+		op.name = "tail_fused";
+		op.tensorBound = false;
+		// read trunk (64ch fp16) + LR input + write BGRX u8 + fp16 state (3ch), SURVEY 8(d)
+		op.bytes = static_cast<double>(B) * (H * W * 64 * 2.0 + H * W * 4.0 + 16.0 * H * W * (4 + 3 * 2));
+		op.flops = 2.0 * B * H * W * (64.0 * 128 + 4.0 * 32 * 12);
+		int *err = m_TcError.as<int>();
+		op.run = [launch, err](cudaStream_t st) { return tail_tc_launch(launch, err, st); };
+		plan.push_back(std::move(op));
+		++m_TcOps;
+		return;
+	}
+	plan.push_back(convOp(ct1, cur, gs, nullptr, m_Mid.get(), 32, H, W, false));
 	{
 		Op op;
 		op.name = "final";

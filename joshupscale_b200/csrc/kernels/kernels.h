@@ -78,6 +78,34 @@ void conv_tc_set_variant(int v);
 void conv_tc_set_flags(int tma_epilogue, int pdl);
 int conv_tc_get_variant();
 
+// ---- fused generator tail (tail_tc.cu): conv_trans_1 GEMM + conv_trans_2 +
+// tanh + bilinear x4 + add + clip + u8 pack + state write in one kernel ------
+struct TailArgs {
+	const __half *in;       // trunk output [batch, h, w, cin_stride] (64 live channels)
+	int cin_stride;
+	const void *weights1;   // conv_trans_1 as 1x1 conv to 128 ch, packed by conv_tc_pack_weights
+	const float *bias1;     // [128]
+	const float *w2;        // [4][3][32]
+	const float *bias2;     // [3]
+	const FrameIO *io;
+	__half *pre_gen_next;   // [batch, 4h, 4w, 4]
+	float *out_raw;         // optional
+	int batch, h, w;
+	int act;
+	float slope;
+	int pdl;
+};
+struct TailTcLaunch {
+	alignas(64) unsigned char map_a[128];
+	alignas(64) unsigned char map_b[128];
+	alignas(8) unsigned char params[160];
+	int grid;
+	unsigned int smem_bytes;
+	int pdl;
+};
+cudaError_t tail_tc_prepare(const TailArgs &a, TailTcLaunch *out);
+cudaError_t tail_tc_launch(const TailTcLaunch &l, int *error_flag, cudaStream_t s);
+
 cudaError_t launch_maxpool2(const __half *in, __half *out, int batch, int h, int w, int c, cudaStream_t s);
 cudaError_t launch_upscale2(const __half *in, __half *out, int batch, int h, int w, int c, cudaStream_t s);
 

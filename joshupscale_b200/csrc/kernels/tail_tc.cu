@@ -1,0 +1,417 @@
+// Fused generator tail on tcgen05: conv_trans_1 (+BN+act) as a 1x1 GEMM to
+// 4 x 32 channels, and - entirely inside its epilogue - conv_trans_2 + bias +
+// tanh + legacy-bilinear x4 of the input frame + add + clip + uint8 BGRX pack +
+// fp16 recurrent-state write.  The [2H,2W,32] intermediate never exists in
+// memory: each epilogue thread owns one LR pixel = 4 mid pixels = a 4x4 block
+// of HR pixels.
+//
+// Replaces, inside the reference's TensorRT engine and C++ glue:
+//   Conv2DTranspose(32,k2,s2)+BN+act            scripts/training/models.py:559-572
+//   Conv2DTranspose(3,k2,s2)+bias, tanh          models.py:573-583
+//   UpscaleLayer(scale=4) + Add + ClipLayer      models.py:584-593; keras_layers.py:46-52, 253-266
+//   PostprocessLayer (truncating uint8 cast)     keras_layers.py:227-230
+//   out_raw -> pre_gen' recurrent output         models.py:808-823
+//   castKernel fp->u8 BGRX, X = 0                core/src/cuda_convert.cc.cu:39-45, 95-108
+//
+// Exactness: everything after the tanh that feeds a byte is fp32 in the
+// reference's operation order with round-to-nearest intrinsics (no FMA
+// contraction), identical to final_kernel in pixel_io.cu.
+#include <cstring>
+
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace ju {
+
+namespace {
+
+using namespace tc;
+
+constexpr int kTileH = 16, kTileW = 8;
+constexpr int kThreads = 192;
+constexpr int kStages = 6;
+constexpr uint32_t kATile = 128u * 128u;  // 128 pixels x 64 ch fp16
+constexpr uint32_t kBBytes = 128u * 128u; // 128 output channels x 64 ch fp16
+
+struct TailParams {
+	int batch, h, w;
+	int tiles_x, tiles_y, total_tiles;
+	int act;
+	float slope;
+	int pdl;
+	const float *bias1;  // [128] folded BN bias of conv_trans_1, channel q*32+o
+	const float *w2;     // [4][3][32] conv_trans_2 (s = i2*2+j2, o, c), fp16-representable values
+	const float *bias2;  // [3]
+	const FrameIO *io;
+	__half *pre_gen_next;  // [batch,4H,4W,4]
+	float *out_raw;        // optional [batch,4H,4W,3]
+	int *error_flag;
+};
+
+__device__ __forceinline__ float preprocess_px(unsigned int v) {
+	return __fsub_rn(__fdiv_rn(static_cast<float>(v), 255.0f), 0.5f);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+tail_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+    const TailParams p) {
+	extern __shared__ uint8_t smem_raw[];
+	const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+	uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+	const uint32_t b_base = smem_base + kStages * kATile;
+	const uint32_t w2_off = kStages * kATile + kBBytes;          // 384 floats
+	const uint32_t bar_base = smem_base + w2_off + 2048u;
+	auto full_bar = [&](int s) { return bar_base + 8u * s; };
+	auto empty_bar = [&](int s) { return bar_base + 8u * (8 + s); };
+	auto tfull_bar = [&](int s) { return bar_base + 8u * (16 + s); };
+	auto tempty_bar = [&](int s) { return bar_base + 8u * (18 + s); };
+	const uint32_t w_bar = bar_base + 8u * 20;
+	const uint32_t tmem_slot = bar_base + 8u * 21;
+
+	const int warp = threadIdx.x >> 5;
+	const int lane = threadIdx.x & 31;
+	constexpr uint32_t kTmemCols = 256;  // 2 accumulator stages x 128 columns
+
+	if (warp == 0 && lane == 0) {
+		for (int s = 0; s < kStages; ++s) {
+			mbar_init(full_bar(s), 1);
+			mbar_init(empty_bar(s), 1);
+		}
+		for (int s = 0; s < 2; ++s) {
+			mbar_init(tfull_bar(s), 1);
+			mbar_init(tempty_bar(s), 4);
+		}
+		mbar_init(w_bar, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	if (warp == 1) {
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+		             "r"(kTmemCols)
+		             : "memory");
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+	}
+	// conv_trans_2 weights + biases -> shared (constants, independent of the previous kernel)
+	{
+		float *w2s = reinterpret_cast<float *>(smem_gen + w2_off);
+		for (int t = threadIdx.x; t < 384; t += kThreads) w2s[t] = p.w2[t];
+		if (threadIdx.x < 3) w2s[384 + threadIdx.x] = p.bias2[threadIdx.x];
+		if (threadIdx.x < 32) w2s[388 + threadIdx.x] = p.bias1[threadIdx.x];
+	}
+	tcgen05_fence_before();
+	__syncthreads();
+	tcgen05_fence_after();
+	uint32_t tmem_base;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+	if (p.pdl) grid_launch_dependents();
+
+	auto decode = [&](int tile, int &b, int &y0, int &x0) {
+		int tx = tile % p.tiles_x;
+		int rest = tile / p.tiles_x;
+		int ty = rest % p.tiles_y;
+		b = rest / p.tiles_y;
+		y0 = ty * kTileH;
+		x0 = tx * kTileW;
+	};
+
+	if (warp == 0) {
+		if (lane == 0) {
+			mbar_arrive_expect_tx(w_bar, kBBytes);
+			tma_load_2d(b_base, &map_b, w_bar, 0, 0);
+			if (p.pdl) grid_dependency_wait();
+			int it = 0;
+			for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+				int b, y0, x0;
+				decode(tile, b, y0, x0);
+				const int s = it % kStages;
+				const uint32_t ph = (it / kStages) & 1;
+				mbar_wait(empty_bar(s), ph ^ 1u, p.error_flag, 1);
+				mbar_arrive_expect_tx(full_bar(s), kATile);
+				tma_load_4d(smem_base + s * kATile, &map_a, full_bar(s), 0, x0, y0, b);
+			}
+		}
+	} else if (warp == 1) {
+		if (lane == 0) {
+			const uint32_t idesc = make_idesc(128);
+			const uint32_t hi = static_cast<uint32_t>(make_smem_desc(0, 1024u, 0) >> 32);
+			const uint32_t lo_flags = 1u << 16;
+			mbar_wait(w_bar, 0, p.error_flag, 2);
+			int it = 0;
+			for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+				const int as = it & 1;
+				const uint32_t aph = (it >> 1) & 1;
+				mbar_wait(tempty_bar(as), aph ^ 1u, p.error_flag, 3);
+				const int s = it % kStages;
+				const uint32_t ph = (it / kStages) & 1;
+				mbar_wait(full_bar(s), ph, p.error_flag, 4);
+				tcgen05_fence_after();
+				const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * 128);
+				const uint32_t a_lo = lo_flags | ((smem_base + s * kATile) >> 4);
+				const uint32_t b_lo = lo_flags | (b_base >> 4);
+#pragma unroll
+				for (int k16 = 0; k16 < 4; ++k16) {
+					const uint64_t a_desc = (static_cast<uint64_t>(hi) << 32) | (a_lo + k16 * 2u);
+					const uint64_t b_desc = (static_cast<uint64_t>(hi) << 32) | (b_lo + k16 * 2u);
+					umma_f16(d_tmem, a_desc, b_desc, idesc, k16 != 0 ? 1u : 0u);
+				}
+				umma_commit(empty_bar(s));
+				umma_commit(tfull_bar(as));
+			}
+		}
+	} else {
+		// ===================== epilogue: one thread = one LR pixel = 4x4 HR pixels =====================
+		const int q4 = warp & 3;
+		const int row = q4 * 32 + lane;
+		const float *w2s = reinterpret_cast<const float *>(smem_gen + w2_off);
+		float bias1[32];
+#pragma unroll
+		for (int c = 0; c < 32; ++c) bias1[c] = w2s[388 + c];
+		const float b2[3] = {w2s[384], w2s[385], w2s[386]};
+		if (p.pdl) grid_dependency_wait();
+		const int H4 = 4 * p.h, W4 = 4 * p.w;
+		int it = 0;
+		for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+			int b, y0, x0;
+			decode(tile, b, y0, x0);
+			const int as = it & 1;
+			const uint32_t aph = (it >> 1) & 1;
+			const int y = y0 + (row >> 3), x = x0 + (row & 7);
+			const bool valid = y < p.h && x < p.w;
+			// bilinear corners of the LR frame (src = dst/4, clamp at the far edge)
+			float cr[4][3];
+			const FrameIO f = p.io[b];
+			if (valid) {
+				const int x1 = min(x + 1, p.w - 1), y1 = min(y + 1, p.h - 1);
+				const uint8_t *r0 = f.in + y * f.in_stride, *r1 = f.in + y1 * f.in_stride;
+				const uchar4 ptl = *reinterpret_cast<const uchar4 *>(r0 + x * 4ll);
+				const uchar4 ptr_ = *reinterpret_cast<const uchar4 *>(r0 + x1 * 4ll);
+				const uchar4 pbl = *reinterpret_cast<const uchar4 *>(r1 + x * 4ll);
+				const uchar4 pbr = *reinterpret_cast<const uchar4 *>(r1 + x1 * 4ll);
+				cr[0][0] = preprocess_px(ptl.x); cr[0][1] = preprocess_px(ptl.y); cr[0][2] = preprocess_px(ptl.z);
+				cr[1][0] = preprocess_px(ptr_.x); cr[1][1] = preprocess_px(ptr_.y); cr[1][2] = preprocess_px(ptr_.z);
+				cr[2][0] = preprocess_px(pbl.x); cr[2][1] = preprocess_px(pbl.y); cr[2][2] = preprocess_px(pbl.z);
+				cr[3][0] = preprocess_px(pbr.x); cr[3][1] = preprocess_px(pbr.y); cr[3][2] = preprocess_px(pbr.z);
+			}
+			mbar_wait(tfull_bar(as), aph, p.error_flag, 5);
+			tcgen05_fence_after();
+			const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>(as * 128);
+#pragma unroll
+			for (int i = 0; i < 2; ++i) {
+				// mid pixels (2y+i, 2x+0) and (2y+i, 2x+1): channels (i*2+j)*32 .. +31
+				uint32_t a0[32], a1[32];
+				__syncwarp();
+				tmem_ld32(taddr + (i * 2 + 0) * 32, a0);
+				tmem_ld32(taddr + (i * 2 + 1) * 32, a1);
+				tmem_ld_wait();
+				if (i == 1) {
+					// all four quarters of the accumulator are in registers
+					tcgen05_fence_before();
+					__syncwarp();
+					if (lane == 0) mbar_arrive(tempty_bar(as));
+				}
+				float m0[32], m1[32];
+#pragma unroll
+				for (int c = 0; c < 32; ++c) {
+					float v0 = __uint_as_float(a0[c]) + bias1[c];
+					float v1 = __uint_as_float(a1[c]) + bias1[c];
+					if (p.act == ACT_RELU) {
+						v0 = fmaxf(v0, 0.f);
+						v1 = fmaxf(v1, 0.f);
+					} else if (p.act == ACT_LRELU) {
+						v0 = v0 >= 0.f ? v0 : v0 * p.slope;
+						v1 = v1 >= 0.f ? v1 : v1 * p.slope;
+					}
+					// the engine's storage contract rounds this activation to fp16
+					m0[c] = __half2float(__float2half_rn(v0));
+					m1[c] = __half2float(__float2half_rn(v1));
+				}
+				// conv_trans_2: z[j][s][o] = sum_c m_j[c] * w2[s][o][c]
+				float z[2][4][3];
+#pragma unroll
+				for (int s = 0; s < 4; ++s)
+#pragma unroll
+					for (int o = 0; o < 3; ++o) z[0][s][o] = z[1][s][o] = 0.f;
+#pragma unroll
+				for (int c4 = 0; c4 < 8; ++c4) {
+#pragma unroll
+					for (int s = 0; s < 4; ++s) {
+#pragma unroll
+						for (int o = 0; o < 3; ++o) {
+							const float4 wv = *reinterpret_cast<const float4 *>(w2s + (s * 3 + o) * 32 + c4 * 4);
+							z[0][s][o] = fmaf(m0[c4 * 4 + 0], wv.x, z[0][s][o]);
+							z[0][s][o] = fmaf(m0[c4 * 4 + 1], wv.y, z[0][s][o]);
+							z[0][s][o] = fmaf(m0[c4 * 4 + 2], wv.z, z[0][s][o]);
+							z[0][s][o] = fmaf(m0[c4 * 4 + 3], wv.w, z[0][s][o]);
+							z[1][s][o] = fmaf(m1[c4 * 4 + 0], wv.x, z[1][s][o]);
+							z[1][s][o] = fmaf(m1[c4 * 4 + 1], wv.y, z[1][s][o]);
+							z[1][s][o] = fmaf(m1[c4 * 4 + 2], wv.z, z[1][s][o]);
+							z[1][s][o] = fmaf(m1[c4 * 4 + 3], wv.w, z[1][s][o]);
+						}
+					}
+				}
+				if (valid) {
+#pragma unroll
+					for (int i2 = 0; i2 < 2; ++i2) {
+						const int R = 2 * i + i2;  // HR row inside the 4x4 block
+						const float ty = static_cast<float>(R) * 0.25f;
+						const int Y = 4 * y + R;
+						uchar4 px[4];
+						__align__(16) __half st[4][4];
+#pragma unroll
+						for (int col = 0; col < 4; ++col) {
+							const int j = col >> 1, j2 = col & 1;
+							const float tx = static_cast<float>(col) * 0.25f;
+							unsigned char o8[3];
+#pragma unroll
+							for (int o = 0; o < 3; ++o) {
+								const float zz = tanhf(z[j][i2 * 2 + j2][o] + b2[o]);
+								const float topv = __fadd_rn(cr[0][o], __fmul_rn(__fsub_rn(cr[1][o], cr[0][o]), tx));
+								const float botv = __fadd_rn(cr[2][o], __fmul_rn(__fsub_rn(cr[3][o], cr[2][o]), tx));
+								const float up = __fadd_rn(topv, __fmul_rn(__fsub_rn(botv, topv), ty));
+								const float r = fminf(fmaxf(__fadd_rn(up, zz), -0.5f), 0.5f);
+								o8[o] = static_cast<unsigned char>(static_cast<int>(__fmul_rn(__fadd_rn(r, 0.5f), 255.0f)));
+								st[col][o] = __float2half_rn(r);
+								if (p.out_raw) {
+									p.out_raw[((static_cast<size_t>(b) * H4 + Y) * W4 + 4 * x + col) * 3 + o] = r;
+								}
+							}
+							st[col][3] = __half(0.f);
+							px[col] = make_uchar4(o8[0], o8[1], o8[2], 0);
+						}
+						uint8_t *orow = f.out + Y * f.out_stride + (4 * x) * 4ll;
+						if ((reinterpret_cast<uintptr_t>(orow) & 15u) == 0) {
+							*reinterpret_cast<uint4 *>(orow) = *reinterpret_cast<const uint4 *>(px);
+						} else {
+#pragma unroll
+							for (int col = 0; col < 4; ++col) reinterpret_cast<uchar4 *>(orow)[col] = px[col];
+						}
+						uint4 *srow = reinterpret_cast<uint4 *>(
+						    p.pre_gen_next + ((static_cast<size_t>(b) * H4 + Y) * W4 + 4 * x) * 4);
+						srow[0] = *reinterpret_cast<const uint4 *>(&st[0][0]);
+						srow[1] = *reinterpret_cast<const uint4 *>(&st[2][0]);
+					}
+				}
+			}
+		}
+	}
+
+	tcgen05_fence_before();
+	__syncthreads();
+	if (warp == 1) {
+		tcgen05_fence_after();
+		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols)
+		             : "memory");
+	}
+}
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encodeTiled() {
+	static EncodeTiledFn fn = nullptr;
+	if (!fn) {
+		void *p = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+		    q != cudaDriverEntryPointSuccess) {
+			return nullptr;
+		}
+		fn = reinterpret_cast<EncodeTiledFn>(p);
+	}
+	return fn;
+}
+
+constexpr uint32_t kSmemBytes = 1024u + kStages * kATile + kBBytes + 2048u + 256u;
+
+}  // namespace
+
+cudaError_t tail_tc_prepare(const TailArgs &a, TailTcLaunch *out) {
+	EncodeTiledFn encode = encodeTiled();
+	if (!encode) return cudaErrorNotSupported;
+	if (a.cin_stride % 64 || a.cin_stride < 64) return cudaErrorInvalidValue;
+	static_assert(sizeof(TailParams) <= sizeof(out->params), "TailTcLaunch::params too small");
+	TailParams p{};
+	p.batch = a.batch;
+	p.h = a.h;
+	p.w = a.w;
+	p.tiles_x = (a.w + kTileW - 1) / kTileW;
+	p.tiles_y = (a.h + kTileH - 1) / kTileH;
+	p.total_tiles = a.batch * p.tiles_x * p.tiles_y;
+	p.act = a.act;
+	p.slope = a.slope;
+	p.pdl = a.pdl;
+	p.bias1 = a.bias1;
+	p.w2 = a.w2;
+	p.bias2 = a.bias2;
+	p.io = a.io;
+	p.pre_gen_next = a.pre_gen_next;
+	p.out_raw = a.out_raw;
+	CUtensorMap mapA, mapB;
+	{
+		cuuint64_t dims[4] = {static_cast<cuuint64_t>(a.cin_stride), static_cast<cuuint64_t>(a.w),
+		    static_cast<cuuint64_t>(a.h), static_cast<cuuint64_t>(a.batch)};
+		cuuint64_t strides[3] = {static_cast<cuuint64_t>(a.cin_stride) * 2,
+		    static_cast<cuuint64_t>(a.w) * a.cin_stride * 2, static_cast<cuuint64_t>(a.h) * a.w * a.cin_stride * 2};
+		cuuint32_t box[4] = {64, kTileW, kTileH, 1};
+		cuuint32_t estr[4] = {1, 1, 1, 1};
+		if (encode(&mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half *>(a.in), dims, strides, box, estr,
+		        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+		        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+			return cudaErrorInvalidValue;
+		}
+	}
+	{
+		// conv_trans_1 weights packed by conv_tc_pack_weights(ksize 1, cin 64, cout 128): [128][64] fp16
+		cuuint64_t dims[2] = {64, 128};
+		cuuint64_t strides[1] = {128};
+		cuuint32_t box[2] = {64, 128};
+		cuuint32_t estr[2] = {1, 1};
+		if (encode(&mapB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(a.weights1), dims, strides, box, estr,
+		        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+		        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+			return cudaErrorInvalidValue;
+		}
+	}
+	std::memcpy(out->map_a, &mapA, 128);
+	std::memcpy(out->map_b, &mapB, 128);
+	std::memcpy(out->params, &p, sizeof(p));
+	int dev = 0, sms = 148;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	out->grid = p.total_tiles < sms ? p.total_tiles : sms;
+	out->smem_bytes = kSmemBytes;
+	out->pdl = a.pdl;
+	return cudaSuccess;
+}
+
+cudaError_t tail_tc_launch(const TailTcLaunch &l, int *error_flag, cudaStream_t s) {
+	static bool attr_set[16] = {false};
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (dev >= 0 && dev < 16 && !attr_set[dev]) {
+		cudaError_t e = cudaFuncSetAttribute(tail_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+		    static_cast<int>(kSmemBytes));
+		if (e != cudaSuccess) return e;
+		attr_set[dev] = true;
+	}
+	CUtensorMap mapA, mapB;
+	TailParams p;
+	std::memcpy(&mapA, l.map_a, 128);
+	std::memcpy(&mapB, l.map_b, 128);
+	std::memcpy(&p, l.params, sizeof(p));
+	p.error_flag = error_flag;
+	cudaLaunchConfig_t cfg{};
+	cfg.gridDim = dim3(l.grid);
+	cfg.blockDim = dim3(kThreads);
+	cfg.dynamicSmemBytes = l.smem_bytes;
+	cfg.stream = s;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = l.pdl ? 1 : 0;
+	return cudaLaunchKernelEx(&cfg, tail_tc_kernel, mapA, mapB, p);
+}
+
+}  // namespace ju

@@ -1,0 +1,148 @@
+// Device-side PTX helpers shared by the tcgen05 kernels (conv_tc.cu, tail_tc.cu):
+// mbarrier, TMA bulk tensor copies, tcgen05 MMA / TMEM access, descriptors.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <cstdint>
+
+namespace ju {
+namespace tc {
+
+// ---- PTX helpers ----------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+	return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+	uint32_t ok;
+	asm volatile(
+	    "{\n\t.reg .pred p;\n\t"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+	    "selp.u32 %0, 1, 0, p;\n\t}"
+	    : "=r"(ok)
+	    : "r"(bar), "r"(parity)
+	    : "memory");
+	return ok;
+}
+
+// Bounded wait: a protocol bug must surface as an error, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int *error_flag, int code) {
+	for (uint32_t i = 0; i < (1u << 22); ++i) {
+		if (mbar_try_wait(bar, parity)) return;
+		if (i > 128) __nanosleep(128);
+	}
+	if (error_flag) atomicExch(error_flag, code);
+	__trap();
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0,
+    int c1, int c2, int c3) {
+	asm volatile(
+	    "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+	    " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+	    "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+	    : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0,
+    int c1) {
+	asm volatile(
+	    "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+	    " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+	    "l"(map), "r"(bar), "r"(c0), "r"(c1)
+	    : "memory");
+}
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2,
+    int c3) {
+	asm volatile(
+	    "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+	    "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+	    : "memory");
+	asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+// the 4 epilogue warps only (threads 64..191)
+__device__ __forceinline__ void epilogue_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() {
+	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+__device__ __forceinline__ void tcgen05_fence_before() {
+	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+	asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+	             : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (fp16 in, fp32 accumulate)
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+    uint32_t accumulate) {
+	asm volatile(
+	    "{\n\t.reg .pred p;\n\t"
+	    "setp.ne.b32 p, %4, 0;\n\t"
+	    "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+	    "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+	    : "memory");
+}
+
+// UMMA shared-memory matrix descriptor, K-major, SWIZZLE_128B (cute
+// UMMA::SmemDescriptor bit layout): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), base_offset [49,52), layout [61,64).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t base_off) {
+	uint64_t d = 0;
+	d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+	d |= static_cast<uint64_t>(1) << 16;
+	d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+	d |= static_cast<uint64_t>(1) << 46;
+	d |= static_cast<uint64_t>(base_off & 7u) << 49;
+	d |= static_cast<uint64_t>(2) << 61;
+	return d;
+}
+
+// Instruction descriptor, kind::f16: D fp32, A/B fp16, both K-major, M=128.
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+	return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+	asm volatile(
+	    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+	    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+	    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+	    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+	      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+	      "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+	      "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+	      "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+	    : "r"(taddr)
+	    : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+
+}  // namespace tc
+}  // namespace ju

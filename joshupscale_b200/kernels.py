@@ -177,3 +177,25 @@ def final(mid: np.ndarray, w2: np.ndarray, bias2: np.ndarray, frames: np.ndarray
     _check(load_library().ju_launch_final(d_m.ptr, d_w.ptr, d_b.ptr, d_f.ptr, d_o.ptr, d_s.ptr,
                                           d_r.ptr, b, h, w, None))
     return d_o.download(), d_s.download(), d_r.download()
+
+
+def tail(trunk: np.ndarray, kt1: np.ndarray, scale1: np.ndarray, bias1: np.ndarray, w2: np.ndarray,
+         bias2: np.ndarray, frames: np.ndarray, act: int = ACT_RELU, slope: float = 0.3):
+    """Fused generator tail.  trunk [B,H,W,64]; kt1 Keras conv_trans_1 kernel (2,2,32,64) with
+    per-filter BN scale1[32] / bias1[32]; w2 Keras conv_trans_2 kernel (2,2,3,32); frames [B,H,W,4] u8.
+    Returns (out_bgrx, pre_gen_next, out_raw) like final()."""
+    b, h, w, _ = frames.shape
+    cout, cin = kt1.shape[2], kt1.shape[3]
+    k1 = np.transpose(np.ascontiguousarray(kt1, np.float32).reshape(4, cout, cin), (2, 0, 1)).reshape(1, 1, cin, 4 * cout)
+    d_t = to_device(trunk.astype(np.float16))
+    d_w1 = to_device(pack_conv_weights(k1, np.tile(np.asarray(scale1, np.float32), 4), 64, IMPL_TCGEN05))
+    d_b1 = to_device(np.tile(np.asarray(bias1, np.float32), 4))
+    d_w2 = to_device(np.ascontiguousarray(w2, np.float32).reshape(4, 3, 32))
+    d_b2 = to_device(np.asarray(bias2, np.float32))
+    d_f = to_device(frames)
+    d_o = DeviceArray((b, 4 * h, 4 * w, 4), np.uint8)
+    d_s = DeviceArray((b, 4 * h, 4 * w, 4), np.float16)
+    d_r = DeviceArray((b, 4 * h, 4 * w, 3), np.float32)
+    _check(load_library().ju_launch_tail(d_t.ptr, d_w1.ptr, d_b1.ptr, d_w2.ptr, d_b2.ptr, d_f.ptr, d_o.ptr,
+                                         d_s.ptr, d_r.ptr, b, h, w, act, slope, None))
+    return d_o.download(), d_s.download(), d_r.download()

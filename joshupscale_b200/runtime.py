@@ -78,6 +78,7 @@ SYMBOLS = {
     "ju_launch_upscale2": (_I, [_VP, _VP, _I, _I, _I, _I, _VP]),
     "ju_launch_warp_s2d": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
     "ju_launch_final": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
+    "ju_launch_tail": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _F, _VP]),
     "ju_dev_alloc": (_I, [C.POINTER(_VP), _U64]),
     "ju_dev_free": (_I, [_VP]),
     "ju_dev_upload": (_I, [_VP, _VP, _U64]),

@@ -112,3 +112,47 @@ def test_engine_runs_on_tensor_cores_and_matches_simt_engine(tmp_path):
     ref, _ = og.Graph(cfg, w, "fp32").run(frames)
     m32, _, p32 = u8_stats(outs["1"][..., :3], ref[..., :3])
     assert m32 <= 2 and p32 >= 45.0
+
+
+@pytest.mark.parametrize("h,w,act", [(16, 8, "relu"), (21, 27, "relu"), (33, 20, "lrelu"), (270, 480, "relu")])
+def test_fused_tail_vs_oracle(h, w, act):
+    """conv_trans_1+BN+act -> conv_trans_2+tanh -> +bilinear x4 -> clip -> u8/state,
+    one tcgen05 kernel, against the unfused oracle ops (fp16-rounded intermediate)."""
+    rng = np.random.default_rng(h * 100 + w)
+    b = 2 if h < 100 else 1
+    trunk = r16(rng.standard_normal((b, h, w, 64)) * 0.5)
+    kt1 = (rng.standard_normal((2, 2, 32, 64)) / 8).astype(np.float32)
+    scale1 = rng.uniform(0.5, 1.5, 32).astype(np.float32)
+    bias1 = (rng.standard_normal(32) * 0.1).astype(np.float32)
+    w2 = r16(rng.standard_normal((2, 2, 3, 32)) * 0.3)
+    b2 = (rng.standard_normal(3) * 0.05).astype(np.float32)
+    frames = rng.integers(0, 256, (b, h, w, 4), dtype=np.uint8)
+    out, state, raw = jk.tail(trunk, kt1, scale1, bias1, w2, b2, frames,
+                              act=jk.ACT_RELU if act == "relu" else jk.ACT_LRELU)
+    mid = og.conv2d_transpose_k2s2(_t(trunk), og.r16(_t(kt1 * scale1[None, None, :, None]))) + _t(bias1)
+    mid = og.r16(og.activation(mid, act))
+    z = torch.tanh(og.conv2d_transpose_k2s2(mid, _t(w2), _t(b2)))
+    want_raw = torch.clamp(og.resize_bilinear_legacy(og.preprocess(frames[..., :3]), 4) + z, -0.5, 0.5).numpy()
+    # the fp16 rounding of the intermediate can flip by one ulp (accumulation order)
+    assert np.abs(raw - want_raw).max() < 2e-3 and np.abs(raw - want_raw).mean() < 2e-5
+    own = ((raw + np.float32(0.5)) * np.float32(255)).astype(np.uint8)
+    np.testing.assert_array_equal(out[..., :3], own)
+    assert int(out[..., 3].max()) == 0
+    np.testing.assert_array_equal(state[..., :3].view(np.uint16), raw.astype(np.float16).view(np.uint16))
+    d = np.abs(out[..., :3].astype(int) - og.postprocess(torch.from_numpy(want_raw)).numpy().astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 0.02
+
+
+def test_fused_tail_engine_equals_unfused_engine(tmp_path):
+    cfg, w, path = make_model(tmp_path, "small")
+    frames = synthetic.frames(cfg.frame_height, cfg.frame_width, 4)
+    outs = {}
+    for fused in ("1", "0"):
+        os.environ["JU_FUSED_TAIL"] = fused
+        try:
+            with jrt.Runtime(path) as rt:
+                outs[fused] = np.stack([rt.process(f) for f in frames])
+        finally:
+            os.environ.pop("JU_FUSED_TAIL", None)
+    m, frac, psnr = u8_stats(outs["1"], outs["0"])
+    assert m <= 1 and frac < 0.03
