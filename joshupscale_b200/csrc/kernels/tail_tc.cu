@@ -2,8 +2,8 @@
 // 4 x 32 channels, and - entirely inside its epilogue - conv_trans_2 + bias +
 // tanh + legacy-bilinear x4 of the input frame + add + clip + uint8 BGRX pack +
 // fp16 recurrent-state write.  The [2H,2W,32] intermediate never exists in
-// memory: each epilogue thread owns one LR pixel = 4 mid pixels = a 4x4 block
-// of HR pixels.
+// memory: 16 epilogue warps, each thread owns one mid-resolution pixel (one of
+// the 4 sub-pixels of an LR pixel) = a 2x2 block of HR pixels.
 //
 // Replaces, inside the reference's TensorRT engine and C++ glue:
 //   Conv2DTranspose(32,k2,s2)+BN+act            scripts/training/models.py:559-572
@@ -28,7 +28,8 @@ namespace {
 using namespace tc;
 
 constexpr int kTileH = 16, kTileW = 8;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 16;  // 4 TMEM lane quarters x 4 sub-pixels
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kStages = 6;
 constexpr uint32_t kATile = 128u * 128u;  // 128 pixels x 64 ch fp16
 constexpr uint32_t kBBytes = 128u * 128u; // 128 output channels x 64 ch fp16
@@ -79,7 +80,7 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 		}
 		for (int s = 0; s < 2; ++s) {
 			mbar_init(tfull_bar(s), 1);
-			mbar_init(tempty_bar(s), 4);
+			mbar_init(tempty_bar(s), kEpiWarps);
 		}
 		mbar_init(w_bar, 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -159,13 +160,16 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 			}
 		}
 	} else {
-		// ===================== epilogue: one thread = one LR pixel = 4x4 HR pixels =====================
-		const int q4 = warp & 3;
+		// ===================== epilogue =====================
+		// 16 warps: warp (quarter, q) owns TMEM lanes quarter*32.. (its 32 LR pixels) and
+		// accumulator columns q*32.. (sub-pixel q = i*2+j of conv_trans_1), i.e. one thread
+		// = one mid-resolution pixel (2y+i, 2x+j) = a 2x2 block of HR pixels.  Four warps
+		// per SM sub-partition hide each other's latency.
+		const int q4 = warp & 3;           // TMEM lane quarter this warp may access
+		const int q = (warp - 2) >> 2;     // sub-pixel handled by this warp
+		const int i = q >> 1, j = q & 1;
 		const int row = q4 * 32 + lane;
 		const float *w2s = reinterpret_cast<const float *>(smem_gen + w2_off);
-		float bias1[32];
-#pragma unroll
-		for (int c = 0; c < 32; ++c) bias1[c] = w2s[388 + c];
 		const float b2[3] = {w2s[384], w2s[385], w2s[386]};
 		if (p.pdl) grid_dependency_wait();
 		const int H4 = 4 * p.h, W4 = 4 * p.w;
@@ -194,102 +198,86 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 			}
 			mbar_wait(tfull_bar(as), aph, p.error_flag, 5);
 			tcgen05_fence_after();
-			const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>(as * 128);
+			const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) +
+			                       static_cast<uint32_t>(as * 128 + q * 32);
+			uint32_t acc[32];
+			__syncwarp();
+			tmem_ld32(taddr, acc);
+			tmem_ld_wait();
+			tcgen05_fence_before();
+			__syncwarp();
+			if (lane == 0) mbar_arrive(tempty_bar(as));
+			float m[32];
 #pragma unroll
-			for (int i = 0; i < 2; ++i) {
-				// mid pixels (2y+i, 2x+0) and (2y+i, 2x+1): channels (i*2+j)*32 .. +31
-				uint32_t a0[32], a1[32];
-				__syncwarp();
-				tmem_ld32(taddr + (i * 2 + 0) * 32, a0);
-				tmem_ld32(taddr + (i * 2 + 1) * 32, a1);
-				tmem_ld_wait();
-				if (i == 1) {
-					// all four quarters of the accumulator are in registers
-					tcgen05_fence_before();
-					__syncwarp();
-					if (lane == 0) mbar_arrive(tempty_bar(as));
-				}
-				float m0[32], m1[32];
+			for (int c4 = 0; c4 < 8; ++c4) {
+				const float4 bv = *reinterpret_cast<const float4 *>(w2s + 388 + c4 * 4);
+				const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
-				for (int c = 0; c < 32; ++c) {
-					float v0 = __uint_as_float(a0[c]) + bias1[c];
-					float v1 = __uint_as_float(a1[c]) + bias1[c];
+				for (int e = 0; e < 4; ++e) {
+					float v = __uint_as_float(acc[c4 * 4 + e]) + bb[e];
 					if (p.act == ACT_RELU) {
-						v0 = fmaxf(v0, 0.f);
-						v1 = fmaxf(v1, 0.f);
+						v = fmaxf(v, 0.f);
 					} else if (p.act == ACT_LRELU) {
-						v0 = v0 >= 0.f ? v0 : v0 * p.slope;
-						v1 = v1 >= 0.f ? v1 : v1 * p.slope;
+						v = v >= 0.f ? v : v * p.slope;
 					}
 					// the engine's storage contract rounds this activation to fp16
-					m0[c] = __half2float(__float2half_rn(v0));
-					m1[c] = __half2float(__float2half_rn(v1));
+					m[c4 * 4 + e] = __half2float(__float2half_rn(v));
 				}
-				// conv_trans_2: z[j][s][o] = sum_c m_j[c] * w2[s][o][c]
-				float z[2][4][3];
+			}
+			// conv_trans_2: z[s][o] = sum_c m[c] * w2[s][o][c], s = i2*2+j2
+			float z[4][3];
 #pragma unroll
-				for (int s = 0; s < 4; ++s)
+			for (int s2 = 0; s2 < 4; ++s2)
 #pragma unroll
-					for (int o = 0; o < 3; ++o) z[0][s][o] = z[1][s][o] = 0.f;
+				for (int o = 0; o < 3; ++o) z[s2][o] = 0.f;
 #pragma unroll
-				for (int c4 = 0; c4 < 8; ++c4) {
+			for (int c4 = 0; c4 < 8; ++c4) {
 #pragma unroll
-					for (int s = 0; s < 4; ++s) {
+				for (int s2 = 0; s2 < 4; ++s2) {
+#pragma unroll
+					for (int o = 0; o < 3; ++o) {
+						const float4 wv = *reinterpret_cast<const float4 *>(w2s + (s2 * 3 + o) * 32 + c4 * 4);
+						z[s2][o] = fmaf(m[c4 * 4 + 0], wv.x, z[s2][o]);
+						z[s2][o] = fmaf(m[c4 * 4 + 1], wv.y, z[s2][o]);
+						z[s2][o] = fmaf(m[c4 * 4 + 2], wv.z, z[s2][o]);
+						z[s2][o] = fmaf(m[c4 * 4 + 3], wv.w, z[s2][o]);
+					}
+				}
+			}
+			if (valid) {
+#pragma unroll
+				for (int i2 = 0; i2 < 2; ++i2) {
+					const int R = 2 * i + i2;  // HR row inside the LR pixel's 4x4 block
+					const float ty = static_cast<float>(R) * 0.25f;
+					const int Y = 4 * y + R;
+					uchar4 px[2];
+					__align__(16) __half st[2][4];
+#pragma unroll
+					for (int j2 = 0; j2 < 2; ++j2) {
+						const float tx = static_cast<float>(2 * j + j2) * 0.25f;
+						unsigned char o8[3];
 #pragma unroll
 						for (int o = 0; o < 3; ++o) {
-							const float4 wv = *reinterpret_cast<const float4 *>(w2s + (s * 3 + o) * 32 + c4 * 4);
-							z[0][s][o] = fmaf(m0[c4 * 4 + 0], wv.x, z[0][s][o]);
-							z[0][s][o] = fmaf(m0[c4 * 4 + 1], wv.y, z[0][s][o]);
-							z[0][s][o] = fmaf(m0[c4 * 4 + 2], wv.z, z[0][s][o]);
-							z[0][s][o] = fmaf(m0[c4 * 4 + 3], wv.w, z[0][s][o]);
-							z[1][s][o] = fmaf(m1[c4 * 4 + 0], wv.x, z[1][s][o]);
-							z[1][s][o] = fmaf(m1[c4 * 4 + 1], wv.y, z[1][s][o]);
-							z[1][s][o] = fmaf(m1[c4 * 4 + 2], wv.z, z[1][s][o]);
-							z[1][s][o] = fmaf(m1[c4 * 4 + 3], wv.w, z[1][s][o]);
-						}
-					}
-				}
-				if (valid) {
-#pragma unroll
-					for (int i2 = 0; i2 < 2; ++i2) {
-						const int R = 2 * i + i2;  // HR row inside the 4x4 block
-						const float ty = static_cast<float>(R) * 0.25f;
-						const int Y = 4 * y + R;
-						uchar4 px[4];
-						__align__(16) __half st[4][4];
-#pragma unroll
-						for (int col = 0; col < 4; ++col) {
-							const int j = col >> 1, j2 = col & 1;
-							const float tx = static_cast<float>(col) * 0.25f;
-							unsigned char o8[3];
-#pragma unroll
-							for (int o = 0; o < 3; ++o) {
-								const float zz = tanhf(z[j][i2 * 2 + j2][o] + b2[o]);
-								const float topv = __fadd_rn(cr[0][o], __fmul_rn(__fsub_rn(cr[1][o], cr[0][o]), tx));
-								const float botv = __fadd_rn(cr[2][o], __fmul_rn(__fsub_rn(cr[3][o], cr[2][o]), tx));
-								const float up = __fadd_rn(topv, __fmul_rn(__fsub_rn(botv, topv), ty));
-								const float r = fminf(fmaxf(__fadd_rn(up, zz), -0.5f), 0.5f);
-								o8[o] = static_cast<unsigned char>(static_cast<int>(__fmul_rn(__fadd_rn(r, 0.5f), 255.0f)));
-								st[col][o] = __float2half_rn(r);
-								if (p.out_raw) {
-									p.out_raw[((static_cast<size_t>(b) * H4 + Y) * W4 + 4 * x + col) * 3 + o] = r;
-								}
+							const float zz = tanhf(z[i2 * 2 + j2][o] + b2[o]);
+							const float topv = __fadd_rn(cr[0][o], __fmul_rn(__fsub_rn(cr[1][o], cr[0][o]), tx));
+							const float botv = __fadd_rn(cr[2][o], __fmul_rn(__fsub_rn(cr[3][o], cr[2][o]), tx));
+							const float up = __fadd_rn(topv, __fmul_rn(__fsub_rn(botv, topv), ty));
+							const float r = fminf(fmaxf(__fadd_rn(up, zz), -0.5f), 0.5f);
+							o8[o] = static_cast<unsigned char>(static_cast<int>(__fmul_rn(__fadd_rn(r, 0.5f), 255.0f)));
+							st[j2][o] = __float2half_rn(r);
+							if (p.out_raw) {
+								p.out_raw[((static_cast<size_t>(b) * H4 + Y) * W4 + 4 * x + 2 * j + j2) * 3 + o] = r;
 							}
-							st[col][3] = __half(0.f);
-							px[col] = make_uchar4(o8[0], o8[1], o8[2], 0);
 						}
-						uint8_t *orow = f.out + Y * f.out_stride + (4 * x) * 4ll;
-						if ((reinterpret_cast<uintptr_t>(orow) & 15u) == 0) {
-							*reinterpret_cast<uint4 *>(orow) = *reinterpret_cast<const uint4 *>(px);
-						} else {
-#pragma unroll
-							for (int col = 0; col < 4; ++col) reinterpret_cast<uchar4 *>(orow)[col] = px[col];
-						}
-						uint4 *srow = reinterpret_cast<uint4 *>(
-						    p.pre_gen_next + ((static_cast<size_t>(b) * H4 + Y) * W4 + 4 * x) * 4);
-						srow[0] = *reinterpret_cast<const uint4 *>(&st[0][0]);
-						srow[1] = *reinterpret_cast<const uint4 *>(&st[2][0]);
+						st[j2][3] = __half(0.f);
+						px[j2] = make_uchar4(o8[0], o8[1], o8[2], 0);
 					}
+					uchar4 *orow = reinterpret_cast<uchar4 *>(f.out + Y * f.out_stride + (4 * x + 2 * j) * 4ll);
+					orow[0] = px[0];
+					orow[1] = px[1];
+					*reinterpret_cast<uint4 *>(
+					    p.pre_gen_next + ((static_cast<size_t>(b) * H4 + Y) * W4 + 4 * x + 2 * j) * 4) =
+					    *reinterpret_cast<const uint4 *>(&st[0][0]);
 				}
 			}
 		}
