@@ -118,7 +118,9 @@ JU_API int ju_launch_preprocess(const uint8_t *frames, const void *flow_prev, vo
 
 /* Generic KxK (K = 1 or 3) SAME convolution, NHWC fp16 in, fp32 accumulate,
  * fused bias / residual / ReLU / LeakyReLU, fp16 or fp32 out, optional
- * 2x2 pixel-shuffle store (ConvTranspose k2s2).  impl: 0 SIMT, 1 tcgen05.
+ * 2x2 pixel-shuffle store (ConvTranspose k2s2; shuffle2 = 1) or fused
+ * MaxPool2D(2) (shuffle2 = 2, tcgen05 only; out is [batch,h/2,w/2,cout_stride]).
+ * impl: 0 SIMT, 1 tcgen05.
  * weights: packed by ju_pack_conv_weights for that impl. */
 JU_API int ju_launch_conv(int impl, const void *in, const void *weights, const float *bias,
     const void *residual, void *out, int batch, int h, int w, int cin_stride, int cin,

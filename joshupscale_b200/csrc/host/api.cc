@@ -343,7 +343,8 @@ int ju_launch_conv(int impl, const void *in, const void *weights, const float *b
 		a.act = act;
 		a.slope = slope;
 		a.out_f32 = out_f32;
-		a.shuffle2 = shuffle2;
+		a.shuffle2 = shuffle2 == 1 ? 1 : 0;
+		a.pool = shuffle2 == 2 ? 1 : 0;
 		auto s = static_cast<cudaStream_t>(stream);
 		if (impl == 0) {
 			JU_CUDA(ju::launch_conv_simt(a, s));

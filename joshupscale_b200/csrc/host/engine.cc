@@ -9,6 +9,10 @@ namespace ju {
 
 namespace {
 
+// thrown by convOp when MaxPool fusion was requested but the tensor-core
+// epilogue cannot provide it for this layer; the caller plans a separate pool
+struct PoolFusionUnavailable {};
+
 int pad64(int c) { return (c + 63) / 64 * 64; }
 int pad16(int c) { return (c + 15) / 16 * 16; }
 
@@ -227,7 +231,7 @@ DeviceBuffer &Engine::newActivation(std::size_t bytes) {
 // ---------------------------------------------------------------------------
 
 Op Engine::convOp(ConvLayer *L, const __half *in, int cinStride, const __half *residual, void *out,
-    int coutStride, int h, int w, bool outF32) {
+    int coutStride, int h, int w, bool outF32, bool pool) {
 	ConvArgs a{};
 	a.in = in;
 	a.weights = L->wSimt.get();
@@ -246,6 +250,7 @@ Op Engine::convOp(ConvLayer *L, const __half *in, int cinStride, const __half *r
 	a.slope = L->slope;
 	a.out_f32 = outF32 ? 1 : 0;
 	a.shuffle2 = L->shuffle2 ? 1 : 0;
+	a.pool = pool ? 1 : 0;
 	if (a.cin > cinStride) throw ModelException("channel stride too small for " + L->name);
 	Op op;
 	op.name = L->name;
@@ -259,13 +264,16 @@ Op Engine::convOp(ConvLayer *L, const __half *in, int cinStride, const __half *r
 		t.cin = pad64(L->cinReal);
 		if (t.cin <= cinStride && conv_tc_supported(t)) {
 			ConvTcLaunch launch;
-			checkCuda(conv_tc_prepare(t, conv_tc_get_variant(), &launch), "conv_tc_prepare");
+			cudaError_t prep = conv_tc_prepare(t, conv_tc_get_variant(), &launch);
+			if (pool && prep != cudaSuccess) throw PoolFusionUnavailable();
+			checkCuda(prep, "conv_tc_prepare");
 			int *err = m_TcError.as<int>();
 			op.run = [launch, err](cudaStream_t s) { return conv_tc_launch(launch, err, s); };
 			++m_TcOps;
 			return op;
 		}
 	}
+	if (pool) throw PoolFusionUnavailable();
 	op.run = [a](cudaStream_t s) { return launch_conv_simt(a, s); };
 	return op;
 }
@@ -318,6 +326,26 @@ void Engine::buildPlan(int parity) {
 		for (int i = 0; i < 2 * n; ++i) {
 			std::string p = "flow/block_" + std::to_string(i + 1);
 			conv(p + "/conv_1");
+			if (i < n && m_ConvImpl == 1 && envInt("JU_FUSED_POOL", 1) != 0 && h % 2 == 0 && w % 2 == 0) {
+				// conv_2 + BN + act + MaxPool2D(2) in one kernel (models.py:386-409)
+				ConvLayer *L = layer(p + "/conv_2");
+				const int os = pad64(L->cout);
+				try {
+					const std::size_t before = actCursor;
+					__half *out = activation(static_cast<std::size_t>(B) * (h / 2) * (w / 2) * os * sizeof(__half));
+					(void) before;
+					Op fused = convOp(L, x, xs, nullptr, out, os, h, w, false, true);
+					fused.name = p + "/conv_2+max_pool";
+					plan.push_back(std::move(fused));
+					x = out;
+					xs = os;
+					h /= 2;
+					w /= 2;
+					continue;
+				} catch (const PoolFusionUnavailable &) {
+					throw ModelException("MaxPool fusion unavailable for " + p + " (set JU_FUSED_POOL=0)");
+				}
+			}
 			conv(p + "/conv_2");
 			const __half *src = x;
 			const int c = xs, hh = h, ww = w;

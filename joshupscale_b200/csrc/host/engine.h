@@ -81,7 +81,7 @@ private:
 	void capture(int parity);
 	ConvLayer *addConv(const std::string &name, const FoldedConv &f, int act, float slope, bool shuffle2);
 	Op convOp(ConvLayer *layer, const __half *in, int cinStride, const __half *residual, void *out,
-	    int coutStride, int h, int w, bool outF32);
+	    int coutStride, int h, int w, bool outF32, bool pool = false);
 	DeviceBuffer &newActivation(std::size_t bytes);
 	void registerTensor(const std::string &name, void *p0, void *p1, int dtype,
 	    std::vector<std::uint64_t> dims, std::size_t bytes, bool writable);

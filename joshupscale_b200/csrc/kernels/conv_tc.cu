@@ -57,7 +57,8 @@ struct TcParams {
 	int base_off_mode;
 	int b_resident;
 	int stages;
-	int tma_epi;  // epilogue through shared memory: TMA residual load + TMA store
+	int tma_epi;  // shared-memory epilogue mode: 0 direct, 1 fp16 N=64, 2 fp16 N=32, 3 fp32 N=32
+	int pool;     // fuse MaxPool2D(2) into the epilogue (tma_epi 1/2, no residual)
 	int pdl;      // launched with programmatic stream serialization
 	uint32_t a_box_bytes, a_region_bytes, stage_bytes, b_slice_bytes;
 	const float *bias;
@@ -90,7 +91,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams &p, int idx) {
 	return t;
 }
 
-template <int KS>
+template <int KS, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
     const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
@@ -103,7 +104,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 	const uint32_t resb_base = smem_base + stages_bytes;
 	const uint32_t resb_bytes = p.b_resident ? static_cast<uint32_t>(taps * p.kb) * p.b_slice_bytes : 0u;
 	// epilogue staging (tma_epi): 2 output tiles + 2 residual tiles of 128 px x 128 B, bias
-	constexpr uint32_t kEpiTile = 128u * 128u;
+	constexpr int kNT = EPI == 1 ? 64 : 32;                       // channels per staged row
+	constexpr uint32_t kRowB = EPI == 2 ? 64u : 128u;             // bytes per staged row
+	constexpr int kChunks = static_cast<int>(kRowB / 16u);        // 16-byte chunks per row
+	constexpr uint32_t kEpiTile = 128u * kRowB;
 	const uint32_t epi_out_base = resb_base + resb_bytes;
 	const uint32_t epi_res_base = epi_out_base + (p.tma_epi ? 2u * kEpiTile : 0u);
 	const uint32_t bias_base = epi_res_base + ((p.tma_epi && p.residual) ? 2u * kEpiTile : 0u);
@@ -258,99 +262,143 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 		const int cpp = p.shuffle2 ? p.cout / 4 : p.cout;  // channels per output pixel
 		const int etid = threadIdx.x - 64;  // 0..127 within the epilogue warps
 		uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic pointer to the aligned base
-		float bias_reg[64];
+		float bias_reg[EPI == 1 ? 64 : 32];
 		if (p.pdl) grid_dependency_wait();
 		int tcount = 0;
 		for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
 			const TileCoord t = decode_tile(p, tile);
 			const int as = tcount & 1;
 			const uint32_t aph = (tcount >> 1) & 1;
-			if (p.tma_epi) {
+			if constexpr (EPI != 0) {
 				// ---- shared-memory epilogue: every global access is a TMA bulk copy ----
-				// thread `row` owns one pixel = one 128-byte row of the 128B-swizzled
-				// staging tiles: 16-byte chunk c of row r lives at r*128 + ((c ^ (r&7)) << 4).
-				// One epilogue warp per SM sub-partition, so latency must be hidden by ILP
-				// inside the thread: bias stays in registers across tiles, the residual
-				// row and both accumulator halves are fetched up-front.
+				// thread `row` owns one pixel = one row (kRowB bytes) of the swizzled staging
+				// tiles; 16-byte chunk c of row r lives at r*kRowB + ((c ^ sw(r)) << 4) with
+				// sw = r&7 (128B swizzle) or (r>>1)&3 (64B swizzle), so the row-per-thread
+				// LDS.128 / STS.128 are bank-conflict free.  One epilogue warp per SM
+				// sub-partition => latency is hidden by ILP inside the thread: bias stays in
+				// registers across tiles, the residual row and the whole accumulator row are
+				// fetched up-front, TMEM is released before the math.
 				if (tcount == 0 || p.n_tiles > 1) {
 #pragma unroll
-					for (int c = 0; c < 64; ++c) bias_reg[c] = p.bias ? __ldg(p.bias + t.n0 + c) : 0.f;
+					for (int c = 0; c < kNT; ++c) bias_reg[c] = p.bias ? __ldg(p.bias + t.n0 + c) : 0.f;
 				}
 				if (etid == 0 && tcount >= 2) {
 					// the bulk store that read staging[as] two tiles ago must have drained
 					asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
 				}
-				const uint32_t sw = static_cast<uint32_t>(row & 7);
-				uint4 res[8];
-				if (p.residual) {
+				const uint32_t sw = EPI == 2 ? static_cast<uint32_t>((row >> 1) & 3) : static_cast<uint32_t>(row & 7);
+				uint4 res[kChunks];
+				if (EPI != 3 && p.residual) {
 					mbar_wait(rfull_bar(as), aph, p.error_flag, 7);
 					const uint4 *res_row = reinterpret_cast<const uint4 *>(
-					    smem_gen + (epi_res_base - smem_base) + as * kEpiTile + row * 128u);
+					    smem_gen + (epi_res_base - smem_base) + as * kEpiTile + row * kRowB);
 #pragma unroll
-					for (int c = 0; c < 8; ++c) res[c] = res_row[c ^ sw];
+					for (int c = 0; c < kChunks; ++c) res[c] = res_row[c ^ sw];
 				}
 				mbar_wait(tfull_bar(as), aph, p.error_flag, 5);
 				tcgen05_fence_after();
-				uint32_t acc0[32], acc1[32];
+				uint32_t acc[kNT];
 				const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
 				                       static_cast<uint32_t>(as * p.nt);
 				__syncwarp();
-				tmem_ld32(taddr, acc0);
-				tmem_ld32(taddr + 32, acc1);
+				tmem_ld32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&acc[0]));
+				if constexpr (kNT == 64) tmem_ld32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&acc[32]));
 				tmem_ld_wait();
 				// TMEM and residual tile are in registers -> hand both back early
 				tcgen05_fence_before();
 				__syncwarp();
 				if (lane == 0) {
 					mbar_arrive(tempty_bar(as));
-					if (p.residual) mbar_arrive(rempty_bar(as));
+					if (EPI != 3 && p.residual) mbar_arrive(rempty_bar(as));
 				}
 				epilogue_barrier();  // staging[as] free (wait_group.read above)
-				uint4 *out_row = reinterpret_cast<uint4 *>(
-				    smem_gen + (epi_out_base - smem_base) + as * kEpiTile + row * 128u);
+				float v[kNT];
 #pragma unroll
-				for (int c = 0; c < 8; ++c) {
-					float v[8];
+				for (int c = 0; c < kNT; ++c) v[c] = __uint_as_float(acc[c]) + bias_reg[c];
+				if (EPI != 3 && p.residual) {
 #pragma unroll
-					for (int e = 0; e < 8; ++e) {
-						v[e] = __uint_as_float(c < 4 ? acc0[c * 8 + e] : acc1[(c - 4) * 8 + e]) + bias_reg[c * 8 + e];
-					}
-					if (p.residual) {
+					for (int c = 0; c < kChunks; ++c) {
 						const __half2 *h2 = reinterpret_cast<const __half2 *>(&res[c]);
 #pragma unroll
 						for (int e = 0; e < 4; ++e) {
 							const float2 f = __half22float2(h2[e]);
-							v[e * 2] += f.x;
-							v[e * 2 + 1] += f.y;
+							v[c * 8 + e * 2] += f.x;
+							v[c * 8 + e * 2 + 1] += f.y;
 						}
 					}
-					if (p.act == ACT_RELU) {
+				}
+				if (p.act == ACT_RELU) {
 #pragma unroll
-						for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
-					} else if (p.act == ACT_LRELU) {
+					for (int c = 0; c < kNT; ++c) v[c] = fmaxf(v[c], 0.f);
+				} else if (p.act == ACT_LRELU) {
 #pragma unroll
-						for (int e = 0; e < 8; ++e) v[e] = v[e] >= 0.f ? v[e] : v[e] * p.slope;
+					for (int c = 0; c < kNT; ++c) v[c] = v[c] >= 0.f ? v[c] : v[c] * p.slope;
+				}
+				uint8_t *out_tile = smem_gen + (epi_out_base - smem_base) + as * kEpiTile;
+				if constexpr (EPI == 3) {
+					// fp32 rows: 32 floats = 8 chunks of 4
+					uint4 *out_row = reinterpret_cast<uint4 *>(out_tile + row * kRowB);
+#pragma unroll
+					for (int c = 0; c < 8; ++c) {
+						uint4 o;
+						o.x = __float_as_uint(v[c * 4 + 0]);
+						o.y = __float_as_uint(v[c * 4 + 1]);
+						o.z = __float_as_uint(v[c * 4 + 2]);
+						o.w = __float_as_uint(v[c * 4 + 3]);
+						out_row[c ^ sw] = o;
 					}
-					uint4 o;
-					__half2 h0 = __floats2half2_rn(v[0], v[1]);
-					__half2 h1 = __floats2half2_rn(v[2], v[3]);
-					__half2 h2o = __floats2half2_rn(v[4], v[5]);
-					__half2 h3 = __floats2half2_rn(v[6], v[7]);
-					o.x = *reinterpret_cast<uint32_t *>(&h0);
-					o.y = *reinterpret_cast<uint32_t *>(&h1);
-					o.z = *reinterpret_cast<uint32_t *>(&h2o);
-					o.w = *reinterpret_cast<uint32_t *>(&h3);
-					out_row[c ^ sw] = o;
+				} else {
+					uint32_t packed[kNT / 2];
+#pragma unroll
+					for (int c = 0; c < kNT / 2; ++c) {
+						__half2 h = __floats2half2_rn(v[2 * c], v[2 * c + 1]);
+						packed[c] = *reinterpret_cast<uint32_t *>(&h);
+					}
+					if (p.pool) {
+						// MaxPool2D(2): lane = (ty%4)*8 + tx, so the 2x2 window partners are
+						// lane^1 (x) and lane^8 (y); max on packed fp16 pairs is exact
+#pragma unroll
+						for (int c = 0; c < kNT / 2; ++c) {
+							__half2 h = *reinterpret_cast<__half2 *>(&packed[c]);
+							uint32_t o1 = __shfl_xor_sync(0xffffffffu, packed[c], 1);
+							h = __hmax2(h, *reinterpret_cast<__half2 *>(&o1));
+							uint32_t hv = *reinterpret_cast<uint32_t *>(&h);
+							uint32_t o8 = __shfl_xor_sync(0xffffffffu, hv, 8);
+							h = __hmax2(h, *reinterpret_cast<__half2 *>(&o8));
+							packed[c] = *reinterpret_cast<uint32_t *>(&h);
+						}
+						if (((row & 1) | ((row >> 3) & 1)) == 0) {
+							// pooled pixel (ty/2, tx/2) of the 8x4 pooled tile
+							const int pr = (row >> 4) * 4 + ((row & 7) >> 1);
+							const uint32_t psw = EPI == 2 ? static_cast<uint32_t>((pr >> 1) & 3) : static_cast<uint32_t>(pr & 7);
+							uint4 *out_row = reinterpret_cast<uint4 *>(out_tile + pr * kRowB);
+#pragma unroll
+							for (int c = 0; c < kChunks; ++c) {
+								out_row[c ^ psw] = make_uint4(packed[c * 4], packed[c * 4 + 1], packed[c * 4 + 2], packed[c * 4 + 3]);
+							}
+						}
+					} else {
+						uint4 *out_row = reinterpret_cast<uint4 *>(out_tile + row * kRowB);
+#pragma unroll
+						for (int c = 0; c < kChunks; ++c) {
+							out_row[c ^ sw] = make_uint4(packed[c * 4], packed[c * 4 + 1], packed[c * 4 + 2], packed[c * 4 + 3]);
+						}
+					}
 				}
 				// make the generic-proxy smem writes visible to the TMA (async proxy)
 				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 				epilogue_barrier();
 				if (etid == 0) {
 					// out-of-range rows/columns of ragged tiles are clipped by the TMA store
-					tma_store_4d(&map_c, epi_out_base + as * kEpiTile, t.n0, t.x0, t.y0, t.b);
+					if (p.pool) {
+						tma_store_4d(&map_c, epi_out_base + as * kEpiTile, t.n0, t.x0 >> 1, t.y0 >> 1, t.b);
+					} else {
+						tma_store_4d(&map_c, epi_out_base + as * kEpiTile, t.n0, t.x0, t.y0, t.b);
+					}
 				}
 				continue;
 			}
+			if constexpr (EPI == 0) {
 			mbar_wait(tfull_bar(as), aph, p.error_flag, 5);
 			tcgen05_fence_after();
 			const int y = t.y0 + (row >> 3), x = t.x0 + (row & 7);
@@ -438,10 +486,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 			tcgen05_fence_before();
 			__syncwarp();
 			if (lane == 0) mbar_arrive(tempty_bar(as));
+			}  // EPI == 0
 		}
 	}
 
-	if (p.tma_epi && threadIdx.x == 64) {
+	if (EPI != 0 && threadIdx.x == 64) {
 		asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 	}
 	tcgen05_fence_before();
@@ -562,11 +611,25 @@ cudaError_t conv_tc_prepare(const ConvArgs &a, int variant, ConvTcLaunch *out) {
 	p.stage_bytes = p.a_region_bytes + (p.b_resident ? 0u : taps * p.b_slice_bytes);
 	// shared-memory epilogue (TMA residual load + TMA store) for the common
 	// fp16, 64-channel-tile, non-shuffled case
-	p.tma_epi = (!a.out_f32 && !a.shuffle2 && p.nt == 64 && a.cout_stride % 8 == 0 && g_TcTmaEpi) ? 1 : 0;
-	p.pdl = g_TcPdl ? 1 : 0;
-	uint32_t epi_bytes = p.tma_epi ? (a.residual ? 4u : 2u) * 128u * 128u : 0u;
+	p.tma_epi = 0;
+	if (g_TcTmaEpi && !a.shuffle2 && a.cout_stride % 8 == 0) {
+		if (!a.out_f32 && p.nt == 64) p.tma_epi = 1;
+		else if (!a.out_f32 && p.nt == 32) p.tma_epi = 2;
+		else if (a.out_f32 && p.nt == 32 && !a.residual) p.tma_epi = 3;
+	}
+	p.pool = 0;
+	if (a.pool) {
+		if ((p.tma_epi != 1 && p.tma_epi != 2) || a.residual || (a.h & 1) || (a.w & 1)) return cudaErrorInvalidValue;
+		p.pool = 1;
+	}
+	auto epiBytes = [&]() -> uint32_t {
+		if (!p.tma_epi) return 0u;
+		const uint32_t tile = 128u * (p.tma_epi == 2 ? 64u : 128u);
+		return (a.residual ? 4u : 2u) * tile;
+	};
+	uint32_t epi_bytes = epiBytes();
 	uint32_t fixed = 1024u + 512u + (p.b_resident ? all_b : 0u) + epi_bytes;
-	if (fixed + 2 * p.stage_bytes > kSmemLimit) {
+	if (fixed + 2 * p.stage_bytes > kSmemLimit && !p.pool) {
 		// streamed-weight layers with big stages: fall back to the register epilogue
 		p.tma_epi = 0;
 		epi_bytes = 0;
@@ -589,22 +652,31 @@ cudaError_t conv_tc_prepare(const ConvArgs &a, int variant, ConvTcLaunch *out) {
 	std::memset(&mapC, 0, sizeof(mapC));
 	std::memset(&mapR, 0, sizeof(mapR));
 	if (p.tma_epi) {
-		// output / residual tensors [batch, h, w, cout_stride] fp16, one 16x8-pixel x 64-channel tile per copy
-		cuuint64_t dims[4] = {static_cast<cuuint64_t>(a.cout_stride), static_cast<cuuint64_t>(a.w),
-		    static_cast<cuuint64_t>(a.h), static_cast<cuuint64_t>(a.batch)};
-		cuuint64_t strides[3] = {static_cast<cuuint64_t>(a.cout_stride) * 2,
-		    static_cast<cuuint64_t>(a.w) * a.cout_stride * 2,
-		    static_cast<cuuint64_t>(a.h) * a.w * a.cout_stride * 2};
-		cuuint32_t box[4] = {64, kTileW, kTileH, 1};
+		// output tensor [batch, oh, ow, cout_stride]; one (pooled) pixel tile x N-tile per copy
+		const bool f32 = p.tma_epi == 3;
+		const cuuint64_t esz = f32 ? 4 : 2;
+		const int oh = p.pool ? a.h / 2 : a.h, ow = p.pool ? a.w / 2 : a.w;
+		cuuint64_t dims[4] = {static_cast<cuuint64_t>(a.cout_stride), static_cast<cuuint64_t>(ow),
+		    static_cast<cuuint64_t>(oh), static_cast<cuuint64_t>(a.batch)};
+		cuuint64_t strides[3] = {static_cast<cuuint64_t>(a.cout_stride) * esz,
+		    static_cast<cuuint64_t>(ow) * a.cout_stride * esz, static_cast<cuuint64_t>(oh) * ow * a.cout_stride * esz};
+		cuuint32_t box[4] = {static_cast<cuuint32_t>(p.nt), static_cast<cuuint32_t>(p.pool ? kTileW / 2 : kTileW),
+		    static_cast<cuuint32_t>(p.pool ? kTileH / 2 : kTileH), 1};
 		cuuint32_t estr[4] = {1, 1, 1, 1};
-		CUresult r = encode(&mapC, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, a.out, dims, strides, box, estr,
-		    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+		const CUtensorMapSwizzle swz = p.tma_epi == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+		CUresult r = encode(&mapC, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, a.out,
+		    dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
 		    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 		if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
 		if (a.residual) {
-			r = encode(&mapR, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half *>(a.residual), dims, strides,
-			    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-			    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+			cuuint64_t rdims[4] = {static_cast<cuuint64_t>(a.cout_stride), static_cast<cuuint64_t>(a.w),
+			    static_cast<cuuint64_t>(a.h), static_cast<cuuint64_t>(a.batch)};
+			cuuint64_t rstrides[3] = {static_cast<cuuint64_t>(a.cout_stride) * 2,
+			    static_cast<cuuint64_t>(a.w) * a.cout_stride * 2, static_cast<cuuint64_t>(a.h) * a.w * a.cout_stride * 2};
+			cuuint32_t rbox[4] = {static_cast<cuuint32_t>(p.nt), kTileW, kTileH, 1};
+			r = encode(&mapR, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half *>(a.residual), rdims, rstrides,
+			    rbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+			    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 			if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
 		}
 	}
@@ -650,12 +722,16 @@ cudaError_t conv_tc_launch(const ConvTcLaunch &l, int *error_flag, cudaStream_t 
 	int dev = 0;
 	cudaGetDevice(&dev);
 	if (dev >= 0 && dev < 16 && !attr_set[dev]) {
-		cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-		    static_cast<int>(kSmemLimit));
-		if (e != cudaSuccess) return e;
-		e = cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-		    static_cast<int>(kSmemLimit));
-		if (e != cudaSuccess) return e;
+		const void *kernels[8] = {
+		    reinterpret_cast<const void *>(conv_tc_kernel<3, 0>), reinterpret_cast<const void *>(conv_tc_kernel<3, 1>),
+		    reinterpret_cast<const void *>(conv_tc_kernel<3, 2>), reinterpret_cast<const void *>(conv_tc_kernel<3, 3>),
+		    reinterpret_cast<const void *>(conv_tc_kernel<1, 0>), reinterpret_cast<const void *>(conv_tc_kernel<1, 1>),
+		    reinterpret_cast<const void *>(conv_tc_kernel<1, 2>), reinterpret_cast<const void *>(conv_tc_kernel<1, 3>)};
+		for (const void *k : kernels) {
+			cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+			    static_cast<int>(kSmemLimit));
+			if (e != cudaSuccess) return e;
+		}
 		attr_set[dev] = true;
 	}
 	CUtensorMap mapA, mapB, mapC, mapR;
@@ -676,8 +752,24 @@ cudaError_t conv_tc_launch(const ConvTcLaunch &l, int *error_flag, cudaStream_t 
 	attr[0].val.programmaticStreamSerializationAllowed = 1;
 	cfg.attrs = attr;
 	cfg.numAttrs = l.pdl ? 1 : 0;
-	if (p.ks == 3) return cudaLaunchKernelEx(&cfg, conv_tc_kernel<3>, mapA, mapB, mapC, mapR, p);
-	return cudaLaunchKernelEx(&cfg, conv_tc_kernel<1>, mapA, mapB, mapC, mapR, p);
+	void *args[5] = {&mapA, &mapB, &mapC, &mapR, &p};
+	const void *fn = nullptr;
+	if (p.ks == 3) {
+		switch (p.tma_epi) {
+		case 1: fn = reinterpret_cast<const void *>(conv_tc_kernel<3, 1>); break;
+		case 2: fn = reinterpret_cast<const void *>(conv_tc_kernel<3, 2>); break;
+		case 3: fn = reinterpret_cast<const void *>(conv_tc_kernel<3, 3>); break;
+		default: fn = reinterpret_cast<const void *>(conv_tc_kernel<3, 0>); break;
+		}
+	} else {
+		switch (p.tma_epi) {
+		case 1: fn = reinterpret_cast<const void *>(conv_tc_kernel<1, 1>); break;
+		case 2: fn = reinterpret_cast<const void *>(conv_tc_kernel<1, 2>); break;
+		case 3: fn = reinterpret_cast<const void *>(conv_tc_kernel<1, 3>); break;
+		default: fn = reinterpret_cast<const void *>(conv_tc_kernel<1, 0>); break;
+		}
+	}
+	return cudaLaunchKernelExC(&cfg, fn, args);
 }
 
 }  // namespace ju

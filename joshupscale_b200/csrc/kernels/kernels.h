@@ -39,6 +39,7 @@ struct ConvArgs {
 	float slope;
 	int out_f32;
 	int shuffle2;            // ConvTranspose k2s2: channel q*(cout/4)+o -> pixel (2y+q/2, 2x+q%2), channel o
+	int pool;                // fuse MaxPool2D(2) into the epilogue: out is [batch, h/2, w/2, cout_stride] (tcgen05 only)
 };
 
 cudaError_t launch_preprocess(const FrameIO *io, const __half *flow_prev, __half *flow_next,

@@ -86,7 +86,7 @@ def pack_conv_weights(kernel: np.ndarray, scale: Optional[np.ndarray], cin_padde
 def conv(x: np.ndarray, kernel: np.ndarray, scale=None, bias=None, residual=None,
          act: int = ACT_NONE, slope: float = 0.3, out_f32: bool = False, shuffle2: bool = False,
          cin_stride: Optional[int] = None, cout_stride: Optional[int] = None,
-         impl: int = IMPL_SIMT) -> np.ndarray:
+         impl: int = IMPL_SIMT, pool: bool = False) -> np.ndarray:
     """x: [B,H,W,Cin] (any float dtype; stored as fp16, zero-padded to cin_stride).
     Returns [B,H,W,Cout] (or [B,2H,2W,Cout/4] with shuffle2) fp16/fp32."""
     lib = load_library()
@@ -104,7 +104,7 @@ def conv(x: np.ndarray, kernel: np.ndarray, scale=None, bias=None, residual=None
         cin_p = cin_stride
     d_w = to_device(pack_conv_weights(kernel, scale, cin_p, impl))
     d_b = to_device(np.asarray(bias, np.float32)) if bias is not None else None
-    oh, ow = (2 * h, 2 * w) if shuffle2 else (h, w)
+    oh, ow = (2 * h, 2 * w) if shuffle2 else ((h // 2, w // 2) if pool else (h, w))
     d_r = None
     if residual is not None:
         r = np.zeros((b, oh, ow, cout_stride), np.float16)
@@ -113,7 +113,7 @@ def conv(x: np.ndarray, kernel: np.ndarray, scale=None, bias=None, residual=None
     d_o = DeviceArray((b, oh, ow, cout_stride), np.float32 if out_f32 else np.float16)
     _check(lib.ju_launch_conv(impl, d_x.ptr, d_w.ptr, d_b.ptr if d_b else None,
                               d_r.ptr if d_r else None, d_o.ptr, b, h, w, cin_stride, cin_p, cout,
-                              cout_stride, ks, act, slope, int(out_f32), int(shuffle2), None))
+                              cout_stride, ks, act, slope, int(out_f32), 2 if pool else int(shuffle2), None))
     sync()
     return d_o.download()[..., :cpp]
 

@@ -156,3 +156,17 @@ def test_fused_tail_engine_equals_unfused_engine(tmp_path):
             os.environ.pop("JU_FUSED_TAIL", None)
     m, frac, psnr = u8_stats(outs["1"], outs["0"])
     assert m <= 1 and frac < 0.03
+
+
+@pytest.mark.parametrize("b,h,w,cin,cout", [(1, 16, 8, 64, 64), (2, 36, 44, 32, 32), (1, 272, 480, 32, 32), (1, 68, 120, 64, 64)])
+def test_conv_tc_fused_maxpool(b, h, w, cin, cout):
+    """conv + BN + ReLU + MaxPool2D(2) in one kernel == maxpool(conv) (models.py:386-409)."""
+    rng = np.random.default_rng(h + w + cin)
+    x = r16(rng.standard_normal((b, h, w, cin)) * 0.5)
+    k = (rng.standard_normal((3, 3, cin, cout)) / np.sqrt(9 * cin)).astype(np.float32)
+    bias = rng.standard_normal(cout).astype(np.float32) * 0.1
+    full = jk.conv(x, k, bias=bias, act=jk.ACT_RELU, impl=jk.IMPL_TCGEN05, cout_stride=64)
+    pooled = jk.conv(x, k, bias=bias, act=jk.ACT_RELU, impl=jk.IMPL_TCGEN05, cout_stride=64, pool=True)
+    want = og.max_pool2(_t(full.astype(np.float32))).numpy().astype(np.float16)
+    assert pooled.shape == (b, h // 2, w // 2, cout)
+    np.testing.assert_array_equal(pooled.view(np.uint16), want.view(np.uint16))
