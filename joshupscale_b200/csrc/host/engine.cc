@@ -326,24 +326,26 @@ void Engine::buildPlan(int parity) {
 		for (int i = 0; i < 2 * n; ++i) {
 			std::string p = "flow/block_" + std::to_string(i + 1);
 			conv(p + "/conv_1");
+			__half *pooled = nullptr;  // MaxPool output, allocated first so both paths share it
+			if (i < n) {
+				const int os = pad64(layer(p + "/conv_2")->cout);
+				pooled = activation(static_cast<std::size_t>(B) * (h / 2) * (w / 2) * os * sizeof(__half));
+			}
 			if (i < n && m_ConvImpl == 1 && envInt("JU_FUSED_POOL", 1) != 0 && h % 2 == 0 && w % 2 == 0) {
 				// conv_2 + BN + act + MaxPool2D(2) in one kernel (models.py:386-409)
 				ConvLayer *L = layer(p + "/conv_2");
 				const int os = pad64(L->cout);
 				try {
-					const std::size_t before = actCursor;
-					__half *out = activation(static_cast<std::size_t>(B) * (h / 2) * (w / 2) * os * sizeof(__half));
-					(void) before;
-					Op fused = convOp(L, x, xs, nullptr, out, os, h, w, false, true);
+					Op fused = convOp(L, x, xs, nullptr, pooled, os, h, w, false, true);
 					fused.name = p + "/conv_2+max_pool";
 					plan.push_back(std::move(fused));
-					x = out;
+					x = pooled;
 					xs = os;
 					h /= 2;
 					w /= 2;
 					continue;
 				} catch (const PoolFusionUnavailable &) {
-					throw ModelException("MaxPool fusion unavailable for " + p + " (set JU_FUSED_POOL=0)");
+					// layer shape not covered by the tensor-core epilogue: separate kernels below
 				}
 			}
 			conv(p + "/conv_2");
@@ -351,7 +353,7 @@ void Engine::buildPlan(int parity) {
 			const int c = xs, hh = h, ww = w;
 			Op op;
 			if (i < n) {
-				__half *out = activation(static_cast<std::size_t>(B) * (h / 2) * (w / 2) * c * sizeof(__half));
+				__half *out = pooled;
 				op.name = p + "/max_pool";
 				op.bytes = static_cast<double>(B) * hh * ww * s.flowFilters[i] * 2.0 * 1.25;
 				op.run = [=](cudaStream_t st) { return launch_maxpool2(src, out, B, hh, ww, c, st); };
