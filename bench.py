@@ -43,6 +43,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 from joshupscale_b200 import config as jcfg  # noqa: E402
+from joshupscale_b200 import sharding  # noqa: E402
 from joshupscale_b200 import synthetic  # noqa: E402
 from joshupscale_b200 import weights as jw  # noqa: E402
 
@@ -187,6 +188,7 @@ def run_ours(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     use_dist = world > 1
     torch = None
+    dist = None
     if use_dist:
         import torch
         import torch.distributed as dist
@@ -209,7 +211,9 @@ def run_ours(args):
     h, w = cfg.frame_height, cfg.frame_width
     in_bytes, out_bytes = h * w * 4, 16 * h * w * 4
 
-    pool = [synthetic.frames(h, w, FRAME_POOL, stream_id=rank * 64 + s) for s in range(streams)]
+    # global stream ids owned by this rank (stream s lives on rank s mod world)
+    my_streams = sharding.streams_for_rank(streams * world, world, rank)
+    pool = [synthetic.frames(h, w, FRAME_POOL, stream_id=sid) for sid in my_streams]
 
     # --- device-resident inputs / outputs (value) ---
     d_in = [[jk.to_device(pool[s][t]) for s in range(streams)] for t in range(FRAME_POOL)]
@@ -259,11 +263,7 @@ def run_ours(args):
         return per_step
 
     def global_max(x):
-        if not use_dist:
-            return x
-        tns = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tns, op=dist.ReduceOp.MAX)
-        return float(tns.item())
+        return sharding.max_over_ranks(x, dist if use_dist else None, "cuda" if use_dist else None)
 
     sampler = ClockSampler(local) if rank == 0 else None
     steps, warmup = args.steps, max(args.warmup, 3)
@@ -329,7 +329,7 @@ def run_ours(args):
                              "restatement of the reference Keras graph (TensorFlow unavailable offline)"}
 
         info = rt.info
-        fps = n_streams_total * steps / total_dev
+        fps = sharding.aggregate_fps(streams, world, steps, total_dev)
         line = {
             "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": steps,
             "warmup": warmup, "ms_per_step": 1000.0 * total_dev / steps, "higher_is_better": True,

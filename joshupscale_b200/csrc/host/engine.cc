@@ -679,20 +679,46 @@ std::vector<ju_op_time> Engine::profileOps(int iters) {
 	}
 	firstOp.push_back(plan.size());
 	std::vector<double> gtotal(labels.size(), 0.0);
-	for (int it = -2; it < iters; ++it) {
+	// each group is captured into its own CUDA graph, so the timing includes the
+	// same device-side launch path (and programmatic edges) as the frame graph
+	// and none of the host's per-launch cost
+	std::vector<cudaGraphExec_t> execs(labels.size(), nullptr);
+	auto destroyExecs = [&] {
+		for (auto &e : execs)
+			if (e) cudaGraphExecDestroy(e);
+	};
+	try {
 		for (std::size_t g = 0; g < labels.size(); ++g) {
-			JU_CUDA(cudaEventRecord(ev[g], m_Stream));
-			for (std::size_t i = firstOp[g]; i < firstOp[g + 1]; ++i) checkCuda(plan[i].run(m_Stream), plan[i].name.c_str());
+			cudaGraph_t graph = nullptr;
+			JU_CUDA(cudaStreamBeginCapture(m_Stream, cudaStreamCaptureModeThreadLocal));
+			cudaError_t err = cudaSuccess;
+			for (std::size_t i = firstOp[g]; i < firstOp[g + 1] && err == cudaSuccess; ++i) err = plan[i].run(m_Stream);
+			cudaError_t endErr = cudaStreamEndCapture(m_Stream, &graph);
+			checkCuda(err, "kernel launch during group capture");
+			checkCuda(endErr, "cudaStreamEndCapture");
+			cudaError_t instErr = cudaGraphInstantiate(&execs[g], graph, 0);
+			cudaGraphDestroy(graph);
+			checkCuda(instErr, "cudaGraphInstantiate");
 		}
-		JU_CUDA(cudaEventRecord(ev[labels.size()], m_Stream));
-		JU_CUDA(cudaStreamSynchronize(m_Stream));
-		if (it < 0) continue;
-		for (std::size_t g = 0; g < labels.size(); ++g) {
-			float ms = 0.f;
-			JU_CUDA(cudaEventElapsedTime(&ms, ev[g], ev[g + 1]));
-			gtotal[g] += ms * 1000.0;
+		for (int it = -2; it < iters; ++it) {
+			for (std::size_t g = 0; g < labels.size(); ++g) {
+				JU_CUDA(cudaEventRecord(ev[g], m_Stream));
+				JU_CUDA(cudaGraphLaunch(execs[g], m_Stream));
+			}
+			JU_CUDA(cudaEventRecord(ev[labels.size()], m_Stream));
+			JU_CUDA(cudaStreamSynchronize(m_Stream));
+			if (it < 0) continue;
+			for (std::size_t g = 0; g < labels.size(); ++g) {
+				float ms = 0.f;
+				JU_CUDA(cudaEventElapsedTime(&ms, ev[g], ev[g + 1]));
+				gtotal[g] += ms * 1000.0;
+			}
 		}
+	} catch (...) {
+		destroyExecs();
+		throw;
 	}
+	destroyExecs();
 	for (std::size_t g = 0; g < labels.size(); ++g) {
 		ju_op_time o;
 		std::memset(&o, 0, sizeof(o));

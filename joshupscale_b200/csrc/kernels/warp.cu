@@ -19,18 +19,14 @@ namespace ju {
 
 namespace {
 
-constexpr int kLrTile = 32;  // LR pixels per block (one LR row segment) -> 128 x 4 HR pixels
+constexpr int kLrTile = 16;  // LR pixels per block (one LR row segment) -> 64x4 HR pixels
 
 __device__ __forceinline__ float preprocess_px(unsigned int v) {
 	return __fsub_rn(__fdiv_rn(static_cast<float>(v), 255.0f), 0.5f);
 }
 
-// One thread = 4 horizontally adjacent HR pixels (one HR row of an LR pixel's
-// 4x4 block): their flow vectors are 8 consecutive floats of the flow head and
-// their 12 warped values are 12 consecutive channels of the S2D row, so loads,
-// index setup and stores are amortised over 4 pixels (the kernel is
-// instruction-issue bound, not bandwidth bound, once the state sits in L2).
-__global__ void __launch_bounds__(128) warp_s2d_kernel(const __half *__restrict__ pre_gen,
+template <bool kTaps, bool kBright>
+__global__ void __launch_bounds__(256) warp_s2d_kernel(const __half *__restrict__ pre_gen,
     const float *__restrict__ flow_head, const FrameIO *__restrict__ io, __half *__restrict__ gen_in,
     float *__restrict__ taps, const float *__restrict__ brightness, int h, int w, int ph, int pw,
     int cstride) {
@@ -42,17 +38,20 @@ __global__ void __launch_bounds__(128) warp_s2d_kernel(const __half *__restrict_
 	const int ly = blockIdx.y;
 	const int lx0 = blockIdx.x * kLrTile;
 	const int t = threadIdx.x;
-	const int i = t >> 5;        // HR row within the 4x4 block
-	const int lxl = t & 31;      // LR pixel within the tile
+	const int i = t >> 6;        // HR row within the 4x4 block
+	const int xx = t & 63;       // HR column within the tile
+	const int lxl = xx >> 2;     // LR pixel within the tile
+	const int j = xx & 3;
 	const int lx = lx0 + lxl;
 	const int H = 4 * h, W = 4 * w;
 
 	// channels 0..2 (current LR frame) and the zero tail 51..63
 	if (t < kLrTile) {
+		int x = lx0 + t;
 		float c0 = 0.f, c1 = 0.f, c2 = 0.f;
-		if (lx < w) {
+		if (x < w) {
 			const FrameIO f = io[b];
-			uchar4 p = *reinterpret_cast<const uchar4 *>(f.in + ly * f.in_stride + lx * 4ll);
+			uchar4 p = *reinterpret_cast<const uchar4 *>(f.in + ly * f.in_stride + x * 4ll);
 			c0 = preprocess_px(p.x);
 			c1 = preprocess_px(p.y);
 			c2 = preprocess_px(p.z);
@@ -65,67 +64,58 @@ __global__ void __launch_bounds__(128) warp_s2d_kernel(const __half *__restrict_
 	}
 
 	if (lx < w) {
-		const int Y = 4 * ly + i;
-		// flow(Y, X) = depth_to_space(head)[Y + 4*top, X + 4*left]: channels (i*4+j)*2 + {dy,dx}
+		const int Y = 4 * ly + i, X = 4 * lx + j;
+		// flow(Y, X) = depth_to_space(head)[Y + 4*top, X + 4*left]
 		const int top = (ph - h) / 2, left = (pw - w) / 2;
-		const float4 *fp = reinterpret_cast<const float4 *>(
-		    flow_head + ((static_cast<size_t>(b) * ph + (ly + top)) * pw + (lx + left)) * 32 + i * 8);
-		const float4 f01 = __ldg(fp), f23 = __ldg(fp + 1);
-		const float fdy[4] = {f01.x, f01.z, f23.x, f23.z};
-		const float fdx[4] = {f01.y, f01.w, f23.y, f23.w};
-		const __half *img = pre_gen + static_cast<size_t>(b) * H * W * 4;
-		const float bright = brightness ? brightness[b] : 0.f;
-		const float fY = static_cast<float>(Y);
-		const float maxfy = static_cast<float>(H - 2), maxfx = static_cast<float>(W - 2);
+		const float2 fl = __ldg(reinterpret_cast<const float2 *>(
+		    flow_head + ((static_cast<size_t>(b) * ph + (ly + top)) * pw + (lx + left)) * 32 +
+		    (i * 4 + j) * 2));
+		// query = grid - flow (dense_image_warp.py:232-237), (dy, dx) order
+		const float qy = __fsub_rn(static_cast<float>(Y), fl.x);
+		const float qx = __fsub_rn(static_cast<float>(X), fl.y);
+		// floor clamped to [0, size-2], alpha clamped to [0, 1] (113-139)
+		const float fy = fminf(fmaxf(0.f, floorf(qy)), static_cast<float>(H - 2));
+		const float fx = fminf(fmaxf(0.f, floorf(qx)), static_cast<float>(W - 2));
+		const float ay = fminf(fmaxf(0.f, __fsub_rn(qy, fy)), 1.f);
+		const float ax = fminf(fmaxf(0.f, __fsub_rn(qx, fx)), 1.f);
+		const int iy = static_cast<int>(fy), ix = static_cast<int>(fx);
+		if (kTaps) {
+			*reinterpret_cast<float4 *>(taps + ((static_cast<size_t>(b) * H + Y) * W + X) * 4) =
+			    make_float4(fy, fx, ay, ax);
+		}
+		// 32-bit element offsets inside one stream's frame (< 2^31 for any supported size)
+		const __half *base = pre_gen + static_cast<size_t>(b) * H * W * 4 +
+		                     (static_cast<unsigned int>(iy) * W + ix) * 4u;
+		// 4 taps x 8 bytes (B,G,R,pad fp16); TL/TR are adjacent in memory
+		const uint2 utl = __ldg(reinterpret_cast<const uint2 *>(base));
+		const uint2 utr = __ldg(reinterpret_cast<const uint2 *>(base + 4));
+		const uint2 ubl = __ldg(reinterpret_cast<const uint2 *>(base + W * 4));
+		const uint2 ubr = __ldg(reinterpret_cast<const uint2 *>(base + W * 4 + 4));
+		const __half *tl = reinterpret_cast<const __half *>(&utl);
+		const __half *tr = reinterpret_cast<const __half *>(&utr);
+		const __half *bl = reinterpret_cast<const __half *>(&ubl);
+		const __half *br = reinterpret_cast<const __half *>(&ubr);
+		const float bright = kBright ? brightness[b] : 0.f;
 #pragma unroll
-		for (int j = 0; j < 4; ++j) {
-			const int X = 4 * lx + j;
-			// query = grid - flow (dense_image_warp.py:232-237), (dy, dx) order
-			const float qy = __fsub_rn(fY, fdy[j]);
-			const float qx = __fsub_rn(static_cast<float>(X), fdx[j]);
-			// floor clamped to [0, size-2], alpha clamped to [0, 1] (113-139)
-			const float fy = fminf(fmaxf(0.f, floorf(qy)), maxfy);
-			const float fx = fminf(fmaxf(0.f, floorf(qx)), maxfx);
-			const float ay = fminf(fmaxf(0.f, __fsub_rn(qy, fy)), 1.f);
-			const float ax = fminf(fmaxf(0.f, __fsub_rn(qx, fx)), 1.f);
-			const int iy = static_cast<int>(fy), ix = static_cast<int>(fx);
-			if (taps) {
-				*reinterpret_cast<float4 *>(taps + ((static_cast<size_t>(b) * H + Y) * W + X) * 4) =
-				    make_float4(fy, fx, ay, ax);
-			}
-			const __half *base = img + (static_cast<unsigned int>(iy) * W + ix) * 4u;
-			// 4 taps x 8 bytes (B,G,R,pad fp16); TL/TR are adjacent in memory
-			const uint2 utl = __ldg(reinterpret_cast<const uint2 *>(base));
-			const uint2 utr = __ldg(reinterpret_cast<const uint2 *>(base + 4));
-			const uint2 ubl = __ldg(reinterpret_cast<const uint2 *>(base + W * 4));
-			const uint2 ubr = __ldg(reinterpret_cast<const uint2 *>(base + W * 4 + 4));
-			const __half *tl = reinterpret_cast<const __half *>(&utl);
-			const __half *tr = reinterpret_cast<const __half *>(&utr);
-			const __half *bl = reinterpret_cast<const __half *>(&ubl);
-			const __half *br = reinterpret_cast<const __half *>(&ubr);
-#pragma unroll
-			for (int c = 0; c < 3; ++c) {
-				const float vtl = __half2float(tl[c]), vtr = __half2float(tr[c]);
-				const float vbl = __half2float(bl[c]), vbr = __half2float(br[c]);
-				const float topv = __fadd_rn(__fmul_rn(ax, __fsub_rn(vtr, vtl)), vtl);
-				const float botv = __fadd_rn(__fmul_rn(ax, __fsub_rn(vbr, vbl)), vbl);
-				float v = __fadd_rn(__fmul_rn(ay, __fsub_rn(botv, topv)), topv);
-				if (brightness) v = __fadd_rn(v, bright);
-				// space_to_depth: channel 3 + (i*4+j)*3 + c  (keras_layers.py:129)
-				tile[lxl][3 + (i * 4 + j) * 3 + c] = __float2half_rn(v);
-			}
+		for (int c = 0; c < 3; ++c) {
+			const float vtl = __half2float(tl[c]), vtr = __half2float(tr[c]);
+			const float vbl = __half2float(bl[c]), vbr = __half2float(br[c]);
+			const float topv = __fadd_rn(__fmul_rn(ax, __fsub_rn(vtr, vtl)), vtl);
+			const float botv = __fadd_rn(__fmul_rn(ax, __fsub_rn(vbr, vbl)), vbl);
+			float v = __fadd_rn(__fmul_rn(ay, __fsub_rn(botv, topv)), topv);
+			if (kBright) v = __fadd_rn(v, bright);
+			// space_to_depth: channel 3 + (i*4+j)*3 + c  (keras_layers.py:129)
+			tile[lxl][3 + (i * 4 + j) * 3 + c] = __float2half_rn(v);
 		}
 	}
 	__syncthreads();
-	// 32 pixels x 128 B = 4 KB: 128 threads x 2 x 16 B, fully coalesced
-#pragma unroll
-	for (int r = 0; r < 2; ++r) {
-		const int v = t + r * 128;
-		const int p = v >> 3, q = v & 7;
+	// 16 pixels x 128 B = 2 KB: 128 threads x 16 B, fully coalesced
+	if (t < kLrTile * 8) {
+		int p = t >> 3, q = t & 7;
 		if (lx0 + p < w) {
-			uint4 val = *reinterpret_cast<const uint4 *>(&tile[p][q * 8]);
+			uint4 v = *reinterpret_cast<const uint4 *>(&tile[p][q * 8]);
 			*reinterpret_cast<uint4 *>(
-			    gen_in + ((static_cast<size_t>(b) * h + ly) * w + lx0 + p) * cstride + q * 8) = val;
+			    gen_in + ((static_cast<size_t>(b) * h + ly) * w + lx0 + p) * cstride + q * 8) = v;
 		}
 	}
 }
@@ -137,8 +127,17 @@ cudaError_t launch_warp_s2d(const __half *pre_gen, const float *flow_head, const
     int cstride, cudaStream_t s) {
 	if (cstride < 64 || cstride % 8) return cudaErrorInvalidValue;
 	dim3 grid((w + kLrTile - 1) / kLrTile, h, batch);
-	warp_s2d_kernel<<<grid, 128, 0, s>>>(pre_gen, flow_head, io, gen_in, taps, brightness, h, w, ph,
-	    pw, cstride);
+	if (taps) {
+		if (brightness) {
+			warp_s2d_kernel<true, true><<<grid, 256, 0, s>>>(pre_gen, flow_head, io, gen_in, taps, brightness, h, w, ph, pw, cstride);
+		} else {
+			warp_s2d_kernel<true, false><<<grid, 256, 0, s>>>(pre_gen, flow_head, io, gen_in, taps, brightness, h, w, ph, pw, cstride);
+		}
+	} else if (brightness) {
+		warp_s2d_kernel<false, true><<<grid, 256, 0, s>>>(pre_gen, flow_head, io, gen_in, taps, brightness, h, w, ph, pw, cstride);
+	} else {
+		warp_s2d_kernel<false, false><<<grid, 256, 0, s>>>(pre_gen, flow_head, io, gen_in, taps, brightness, h, w, ph, pw, cstride);
+	}
 	return cudaGetLastError();
 }
 
