@@ -133,6 +133,8 @@ def preset(name: str) -> ModelConfig:
         "tiny": ModelConfig(frame_height=21, frame_width=27, gen_blocks=2,
                             flow_filters=(8, 16, 16, 32, 16, 16, 8)),
         "small": ModelConfig(frame_height=46, frame_width=72, gen_blocks=3),
+        "small_bright": ModelConfig(frame_height=46, frame_width=72, gen_blocks=2,
+                                    normalize_brightness=True, flow_num_inputs=3),
         "small_resnet": ModelConfig(frame_height=46, frame_width=72, gen_blocks=2,
                                     flow_arch="resnet", flow_resnet_blocks=2,
                                     flow_pad_factor=0),

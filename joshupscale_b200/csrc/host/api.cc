@@ -316,7 +316,7 @@ int ju_launch_preprocess(const uint8_t *frames, const void *flow_prev, void *flo
 		TempIo io(frames, nullptr, batch, h, w);
 		auto s = static_cast<cudaStream_t>(stream);
 		JU_CUDA(ju::launch_preprocess(io.get(), static_cast<const __half *>(flow_prev),
-		    static_cast<__half *>(flow_next), batch, h, w, ph, pw, k, cstride, s));
+		    static_cast<__half *>(flow_next), nullptr, batch, h, w, ph, pw, k, cstride, s));
 		JU_CUDA(cudaStreamSynchronize(s));
 	});
 }

@@ -187,6 +187,7 @@ void Engine::allocate() {
 	const ModelSpec &s = m_Spec;
 	const std::uint64_t B = m_Batch, H = s.frameH, W = s.frameW, PH = s.padH, PW = s.padW;
 	m_TcError = DeviceBuffer(sizeof(int));
+	m_Brightness = DeviceBuffer(sizeof(float) * B);
 	m_IoHost = PinnedBuffer(sizeof(FrameIO) * B);
 	m_IoDev = DeviceBuffer(sizeof(FrameIO) * B);
 	m_InStage = DeviceBuffer(B * H * W * 4);
@@ -299,13 +300,25 @@ void Engine::buildPlan(int parity) {
 	const __half *preGenPrev = m_PreGen[parity].as<__half>();
 	__half *preGenNext = m_PreGen[parity ^ 1].as<__half>();
 
+	const float *bright = nullptr;
+	if (s.normalizeBrightness) {
+		// models.py:772-779: scalar per stream, subtracted from the flow input and the
+		// recurrent state, added back to the warped frame
+		float *bout = m_Brightness.as<float>();
+		bright = bout;
+		Op op;
+		op.name = "brightness";
+		op.bytes = static_cast<double>(B) * H * W * 4.0;
+		op.run = [=](cudaStream_t st) { return launch_brightness(io, bout, B, H, W, st); };
+		plan.push_back(std::move(op));
+	}
 	{
 		Op op;
 		op.name = "preprocess";
 		const int k = s.flowInputs, cs = m_FlowCStride;
 		op.bytes = static_cast<double>(B) * (H * W * 4.0 + PH * PW * (3.0 * (k - 1) * 2 + 3.0 * k * 2));
 		op.run = [=](cudaStream_t st) {
-			return launch_preprocess(io, flowPrev, flowNext, B, H, W, PH, PW, k, cs, st);
+			return launch_preprocess(io, flowPrev, flowNext, bright, B, H, W, PH, PW, k, cs, st);
 		};
 		plan.push_back(std::move(op));
 	}
@@ -393,7 +406,7 @@ void Engine::buildPlan(int parity) {
 		// read state (3ch fp16) + read flow (2 x fp32 here) + write warped (3ch fp16), SURVEY 8(d)
 		op.bytes = static_cast<double>(B) * 16.0 * H * W * (3 * 2 + 2 * 4 + 3 * 2);
 		op.run = [=](cudaStream_t st) {
-			return launch_warp_s2d(preGenPrev, head, io, genIn, nullptr, nullptr, B, H, W, PH, PW, 64, st);
+			return launch_warp_s2d(preGenPrev, head, io, genIn, nullptr, bright, B, H, W, PH, PW, 64, st);
 		};
 		plan.push_back(std::move(op));
 	}
@@ -430,6 +443,7 @@ void Engine::buildPlan(int parity) {
 		ta.io = io;
 		ta.pre_gen_next = preGenNext;
 		ta.out_raw = nullptr;
+		ta.brightness = bright;
 		ta.batch = B;
 		ta.h = H;
 		ta.w = W;
@@ -460,7 +474,7 @@ void Engine::buildPlan(int parity) {
 		op.bytes = static_cast<double>(B) * (4.0 * H * W * 32 * 2 + H * W * 4.0 + 16.0 * H * W * (4 + 3 * 2));
 		op.flops = 2.0 * B * 4.0 * H * W * 32 * 12;
 		op.run = [=](cudaStream_t st) {
-			return launch_final(mid, w2, b2, io, preGenNext, nullptr, nullptr, B, H, W, st);
+			return launch_final(mid, w2, b2, io, preGenNext, nullptr, bright, B, H, W, st);
 		};
 		plan.push_back(std::move(op));
 	}

@@ -99,6 +99,7 @@ private:
 	PinnedBuffer m_IoHost;
 	DeviceBuffer m_IoDev;
 	DeviceBuffer m_TcError;
+	DeviceBuffer m_Brightness;
 	int m_TcOps = 0;
 	DeviceBuffer m_InStage, m_OutStage;
 	std::vector<ju_image> m_LastOutputs;

@@ -42,8 +42,13 @@ struct ConvArgs {
 	int pool;                // fuse MaxPool2D(2) into the epilogue: out is [batch, h/2, w/2, cout_stride] (tcgen05 only)
 };
 
+// brightness (optional, [batch] fp32 or nullptr): subtracted from the flow-net input
 cudaError_t launch_preprocess(const FrameIO *io, const __half *flow_prev, __half *flow_next,
-    int batch, int h, int w, int ph, int pw, int k, int cstride, cudaStream_t s);
+    const float *brightness, int batch, int h, int w, int ph, int pw, int k, int cstride, cudaStream_t s);
+
+// normalize_brightness (scripts/training/models.py:772-779; utils.py:151):
+// out[b] = mean over (h, w, c) of cur * BGR_LUMA * 3, deterministic summation order
+cudaError_t launch_brightness(const FrameIO *io, float *out, int batch, int h, int w, cudaStream_t s);
 
 cudaError_t launch_conv_simt(const ConvArgs &a, cudaStream_t s);
 // bytes of the SIMT weight layout [tap][cin_padded][cout] fp16
@@ -91,6 +96,7 @@ struct TailArgs {
 	const FrameIO *io;
 	__half *pre_gen_next;   // [batch, 4h, 4w, 4]
 	float *out_raw;         // optional
+	const float *brightness;  // optional [batch]: subtracted from the recurrent state
 	int batch, h, w;
 	int act;
 	float slope;

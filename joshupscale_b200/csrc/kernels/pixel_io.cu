@@ -171,10 +171,42 @@ __global__ void final_kernel(const __half *__restrict__ mid, const float *__rest
 }  // namespace
 
 cudaError_t launch_preprocess(const FrameIO *io, const __half *flow_prev, __half *flow_next,
-    int batch, int h, int w, int ph, int pw, int k, int cstride, cudaStream_t s) {
+    const float *brightness, int batch, int h, int w, int ph, int pw, int k, int cstride, cudaStream_t s) {
 	dim3 block(128);
 	dim3 grid((pw + 127) / 128, ph, batch);
-	preprocess_kernel<<<grid, block, 0, s>>>(io, flow_prev, flow_next, nullptr, h, w, ph, pw, k, cstride);
+	preprocess_kernel<<<grid, block, 0, s>>>(io, flow_prev, flow_next, brightness, h, w, ph, pw, k, cstride);
+	return cudaGetLastError();
+}
+
+namespace {
+
+// one block per stream; fixed thread-strided order + fixed tree => bit-stable
+__global__ void __launch_bounds__(1024) brightness_kernel(const FrameIO *__restrict__ io, float *__restrict__ out,
+    int h, int w) {
+	__shared__ float part[1024];
+	const FrameIO f = io[blockIdx.x];
+	float acc = 0.f;
+	const int n = h * w;
+	for (int p = threadIdx.x; p < n; p += 1024) {
+		const int y = p / w, x = p - y * w;
+		const uchar4 px = *reinterpret_cast<const uchar4 *>(f.in + y * f.in_stride + x * 4ll);
+		// BGR_LUMA = [0.1140, 0.5870, 0.2989] (utils.py:151), times 3 (models.py:776)
+		acc += preprocess_px(px.x) * 0.1140f * 3.f + preprocess_px(px.y) * 0.5870f * 3.f +
+		       preprocess_px(px.z) * 0.2989f * 3.f;
+	}
+	part[threadIdx.x] = acc;
+	__syncthreads();
+	for (int s = 512; s > 0; s >>= 1) {
+		if (threadIdx.x < s) part[threadIdx.x] += part[threadIdx.x + s];
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) out[blockIdx.x] = part[0] / static_cast<float>(3 * n);
+}
+
+}  // namespace
+
+cudaError_t launch_brightness(const FrameIO *io, float *out, int batch, int h, int w, cudaStream_t s) {
+	brightness_kernel<<<batch, 1024, 0, s>>>(io, out, h, w);
 	return cudaGetLastError();
 }
 

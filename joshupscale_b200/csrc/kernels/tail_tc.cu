@@ -46,6 +46,7 @@ struct TailParams {
 	const FrameIO *io;
 	__half *pre_gen_next;  // [batch,4H,4W,4]
 	float *out_raw;        // optional [batch,4H,4W,3]
+	const float *brightness;  // optional [batch]
 	int *error_flag;
 };
 
@@ -206,6 +207,7 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 			// bilinear corners of the LR frame (src = dst/4, clamp at the far edge)
 			float cr[4][3];
 			const FrameIO f = p.io[b];
+			const float bright = p.brightness ? p.brightness[b] : 0.f;
 			if (valid) {
 				const int x1 = min(x + 1, p.w - 1), y1 = min(y + 1, p.h - 1);
 				const uint8_t *r0 = f.in + y * f.in_stride, *r1 = f.in + y1 * f.in_stride;
@@ -293,7 +295,7 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 							const float up = __fadd_rn(topv, __fmul_rn(__fsub_rn(botv, topv), ty));
 							const float r = fminf(fmaxf(__fadd_rn(up, zz), -0.5f), 0.5f);
 							o8[o] = static_cast<unsigned char>(static_cast<int>(__fmul_rn(__fadd_rn(r, 0.5f), 255.0f)));
-							st[j2][o] = __float2half_rn(r);
+							st[j2][o] = __float2half_rn(r - bright);
 							if (p.out_raw) {
 								p.out_raw[((static_cast<size_t>(b) * H4 + Y) * W4 + 4 * x + 2 * j + j2) * 3 + o] = r;
 							}
@@ -364,6 +366,7 @@ cudaError_t tail_tc_prepare(const TailArgs &a, TailTcLaunch *out) {
 	p.io = a.io;
 	p.pre_gen_next = a.pre_gen_next;
 	p.out_raw = a.out_raw;
+	p.brightness = a.brightness;
 	CUtensorMap mapA, mapB;
 	{
 		cuuint64_t dims[4] = {static_cast<cuuint64_t>(a.cin_stride), static_cast<cuuint64_t>(a.w),

@@ -33,7 +33,8 @@ def _run_gpu(path, frames, batch=1):
 
 
 @pytest.mark.parametrize("preset,conditioned,nframes", [
-    ("tiny", True, 6), ("small", True, 6), ("small", False, 4), ("small_resnet", True, 4)])
+    ("tiny", True, 6), ("small", True, 6), ("small", False, 4), ("small_resnet", True, 4),
+    ("small_bright", True, 5)])
 def test_recurrent_parity_small(tmp_path, preset, conditioned, nframes):
     cfg, w, path = make_model(tmp_path, preset, conditioned=conditioned)
     frames = synthetic.frames(cfg.frame_height, cfg.frame_width, nframes)

@@ -210,3 +210,24 @@ def test_gmac_table_matches_survey():
     assert abs(cfg.flow_gmacs() - 17.90) < 0.01
     assert abs(cfg.gen_gmacs() - 234.39) < 0.01
     assert abs(cfg.gflop_per_frame() - 504.6) < 0.1
+
+
+def test_brightness_normalisation_oracle_wiring():
+    """normalize_brightness (models.py:772-779, 802-810): b is subtracted from the
+    flow input and the stored state, added to the warped frame; the output is unchanged
+    by a constant state offset only through those paths."""
+    cfg = jcfg.preset("small_bright")
+    w = jw.init_weights(cfg, seed=9)
+    frames = synthetic.frames(cfg.frame_height, cfg.frame_width, 2)
+    frames[..., :3] = np.clip(frames[..., :3].astype(int) + 60, 0, 255).astype(np.uint8)  # bright scene
+    g = og.Graph(cfg, w, "fp32")
+    state = g.zero_state()
+    _, state, aux = g.step(frames[0:1], state)
+    cur = og.preprocess(frames[0:1, ..., :3])
+    b = float((cur * torch.tensor(og.BGR_LUMA) * 3).mean())
+    assert b > 0.1
+    np.testing.assert_allclose(state["pre_gen"].numpy(), (aux["out_raw"] - b).numpy(), atol=1e-6)
+    top, left = cfg.pad_top, cfg.pad_left
+    inner = state["last_frames"][0][0, top:top + cfg.frame_height, left:left + cfg.frame_width]
+    np.testing.assert_allclose(inner.numpy(), (cur[0] - b).numpy(), atol=1e-6)
+    assert len(state["last_frames"]) == cfg.flow_num_inputs - 1 == 2
