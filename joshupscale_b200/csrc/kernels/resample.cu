@@ -39,39 +39,50 @@ __global__ void maxpool2_kernel(const __half *__restrict__ in, __half *__restric
 	reinterpret_cast<uint4 *>(out)[idx] = r;
 }
 
+// One thread = 8 channels of one INPUT pixel -> the 2x2 block of output pixels
+// it anchors.  With scale 2 the legacy (asymmetric) bilinear weights are 0 or
+// 0.5, so out(2y,2x) = in(y,x) exactly and the other three are single lerps of
+// the same four inputs (a b / c d); the reference's operation order
+// (top = tl + (tr-tl)*tx ; bot likewise ; top + (bot-top)*ty, fp32) is kept, so
+// results are bit-identical to evaluating the general formula per output.
 __global__ void upscale2_kernel(const __half *__restrict__ in, __half *__restrict__ out, int h,
     int w, int c8, size_t total) {
 	size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
 	if (idx >= total) return;
 	int cv = idx % c8;
 	size_t p = idx / c8;
-	int ow = 2 * w, oh = 2 * h;
-	int ox = p % ow;
-	size_t q = p / ow;
-	int oy = q % oh;
-	size_t b = q / oh;
-	int y0 = oy >> 1, x0 = ox >> 1;
-	int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
-	float ty = (oy & 1) * 0.5f, tx = (ox & 1) * 0.5f;
+	int x = p % w;
+	size_t q = p / w;
+	int y = q % h;
+	size_t b = q / h;
+	int y1 = min(y + 1, h - 1), x1 = min(x + 1, w - 1);
 	const uint4 *src = reinterpret_cast<const uint4 *>(in);
-	uint4 tl = src[((b * h + y0) * w + x0) * c8 + cv];
-	uint4 tr = src[((b * h + y0) * w + x1) * c8 + cv];
-	uint4 bl = src[((b * h + y1) * w + x0) * c8 + cv];
-	uint4 br = src[((b * h + y1) * w + x1) * c8 + cv];
-	const __half *ptl = reinterpret_cast<const __half *>(&tl);
-	const __half *ptr_ = reinterpret_cast<const __half *>(&tr);
-	const __half *pbl = reinterpret_cast<const __half *>(&bl);
-	const __half *pbr = reinterpret_cast<const __half *>(&br);
-	__align__(16) __half r[8];
+	const uint4 va = src[((b * h + y) * w + x) * c8 + cv];
+	const uint4 vb = src[((b * h + y) * w + x1) * c8 + cv];
+	const uint4 vc = src[((b * h + y1) * w + x) * c8 + cv];
+	const uint4 vd = src[((b * h + y1) * w + x1) * c8 + cv];
+	const __half *pa = reinterpret_cast<const __half *>(&va);
+	const __half *pb = reinterpret_cast<const __half *>(&vb);
+	const __half *pc = reinterpret_cast<const __half *>(&vc);
+	const __half *pd = reinterpret_cast<const __half *>(&vd);
+	__align__(16) __half r01[8], r10[8], r11[8];
 #pragma unroll
 	for (int e = 0; e < 8; ++e) {
-		float a = __half2float(ptl[e]), bq = __half2float(ptr_[e]);
-		float c = __half2float(pbl[e]), d = __half2float(pbr[e]);
-		float topv = __fadd_rn(a, __fmul_rn(__fsub_rn(bq, a), tx));
-		float botv = __fadd_rn(c, __fmul_rn(__fsub_rn(d, c), tx));
-		r[e] = __float2half_rn(__fadd_rn(topv, __fmul_rn(__fsub_rn(botv, topv), ty)));
+		const float a = __half2float(pa[e]), bq = __half2float(pb[e]);
+		const float c = __half2float(pc[e]), d = __half2float(pd[e]);
+		const float top = __fadd_rn(a, __fmul_rn(__fsub_rn(bq, a), 0.5f));   // tx = 0.5
+		const float bot = __fadd_rn(c, __fmul_rn(__fsub_rn(d, c), 0.5f));
+		r01[e] = __float2half_rn(top);                                        // (2y, 2x+1): ty = 0
+		r10[e] = __float2half_rn(__fadd_rn(a, __fmul_rn(__fsub_rn(c, a), 0.5f)));  // (2y+1, 2x): tx = 0
+		r11[e] = __float2half_rn(__fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), 0.5f)));
 	}
-	reinterpret_cast<uint4 *>(out)[idx] = *reinterpret_cast<const uint4 *>(r);
+	uint4 *dst = reinterpret_cast<uint4 *>(out);
+	const size_t ow = 2 * static_cast<size_t>(w);
+	const size_t o00 = ((b * 2 * h + 2 * y) * ow + 2 * x) * c8 + cv;
+	dst[o00] = va;                                            // (2y, 2x): tx = ty = 0 -> in(y, x)
+	dst[o00 + c8] = *reinterpret_cast<const uint4 *>(r01);
+	dst[o00 + ow * c8] = *reinterpret_cast<const uint4 *>(r10);
+	dst[o00 + ow * c8 + c8] = *reinterpret_cast<const uint4 *>(r11);
 }
 
 }  // namespace
@@ -85,7 +96,7 @@ cudaError_t launch_maxpool2(const __half *in, __half *out, int batch, int h, int
 
 cudaError_t launch_upscale2(const __half *in, __half *out, int batch, int h, int w, int c, cudaStream_t s) {
 	if (c % 8) return cudaErrorInvalidValue;
-	size_t total = static_cast<size_t>(batch) * (2 * h) * (2 * w) * (c / 8);
+	size_t total = static_cast<size_t>(batch) * h * w * (c / 8);  // one thread per input pixel-vector
 	upscale2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(in, out, h, w, c / 8, total);
 	return cudaGetLastError();
 }
