@@ -41,7 +41,8 @@ namespace {
 
 constexpr int kTileH = 16;  // pixel rows per M tile (= UMMA core-matrix groups)
 constexpr int kTileW = 8;   // pixel columns per M tile (= rows per core-matrix group)
-constexpr int kThreads = 192;
+constexpr int kThreads = 192;       // 2 control warps + 4 epilogue warps
+constexpr int kThreadsWide = 320;   // 2 control warps + 8 epilogue warps (fp16 N=64 epilogue)
 constexpr int kMaxStages = 8;
 constexpr uint32_t kSmemLimit = 227 * 1024;
 
@@ -92,7 +93,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams &p, int idx) {
 }
 
 template <int KS, int EPI>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(EPI == 1 ? kThreadsWide : kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
     const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
     const TcParams p) {
@@ -132,9 +133,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 		}
 		for (int s = 0; s < 2; ++s) {
 			mbar_init(tfull_bar(s), 1);
-			mbar_init(tempty_bar(s), 4);  // one arrival per epilogue warp
+			mbar_init(tempty_bar(s), EPI == 1 ? 8 : 4);  // one arrival per epilogue warp
 			mbar_init(rfull_bar(s), 1);
-			mbar_init(rempty_bar(s), 4);
+			mbar_init(rempty_bar(s), EPI == 1 ? 8 : 4);
 		}
 		mbar_init(w_bar, 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -210,7 +211,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 		// stream is the critical path: descriptors are split into a constant high
 		// word and a 32-bit low word (start address >> 4) that only needs one add
 		// per MMA; tap / k offsets are compile-time constants after unrolling.
-		if (lane == 0) {
+		{
+			// the whole warp stays converged; one elected lane issues the MMAs and commits
 			const uint32_t idesc = make_idesc(p.nt);
 			const uint32_t a_sbo = static_cast<uint32_t>(p.pitch) * 128u;
 			const uint32_t a_hi = static_cast<uint32_t>(make_smem_desc(0, a_sbo, 0) >> 32);
@@ -239,6 +241,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 					                                               : stage + p.a_region_bytes) >> 4);
 					const uint32_t b_tap16 = p.b_resident ? b_slice16 * p.kb : b_slice16;
 					uint32_t first = kbi == 0 ? 0u : 1u;
+					if (elect_one_sync()) {
 #pragma unroll
 					for (int tap = 0; tap < taps; ++tap) {
 						const uint32_t a_tap = a_lo + (tap / KS) * row_off + (tap % KS) * 8u;
@@ -251,8 +254,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 						}
 					}
 					umma_commit(empty_bar(s));  // frees the stage when these MMAs have read it
+					if (kbi == p.kb - 1) umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
+					}
+					__syncwarp();
 				}
-				umma_commit(tfull_bar(as));  // accumulator complete -> epilogue
 			}
 		}
 	} else {
@@ -260,9 +265,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 		const int q = warp & 3;  // TMEM lane quarter this warp may access
 		const int row = q * 32 + lane;
 		const int cpp = p.shuffle2 ? p.cout / 4 : p.cout;  // channels per output pixel
-		const int etid = threadIdx.x - 64;  // 0..127 within the epilogue warps
+		const int etid = threadIdx.x - 64;  // index within the epilogue warps
+		const int half = EPI == 1 ? ((warp - 2) >> 2) : 0;  // 32-channel half handled by this warp
 		uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic pointer to the aligned base
-		float bias_reg[EPI == 1 ? 64 : 32];
+		float bias_reg[32];
 		if (p.pdl) grid_dependency_wait();
 		int tcount = 0;
 		for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
@@ -271,38 +277,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 			const uint32_t aph = (tcount >> 1) & 1;
 			if constexpr (EPI != 0) {
 				// ---- shared-memory epilogue: every global access is a TMA bulk copy ----
-				// thread `row` owns one pixel = one row (kRowB bytes) of the swizzled staging
-				// tiles; 16-byte chunk c of row r lives at r*kRowB + ((c ^ sw(r)) << 4) with
-				// sw = r&7 (128B swizzle) or (r>>1)&3 (64B swizzle), so the row-per-thread
-				// LDS.128 / STS.128 are bank-conflict free.  One epilogue warp per SM
-				// sub-partition => latency is hidden by ILP inside the thread: bias stays in
-				// registers across tiles, the residual row and the whole accumulator row are
-				// fetched up-front, TMEM is released before the math.
+				// A thread owns 32 channels of one pixel: the fp16 N=64 mode runs 8 epilogue
+				// warps (two per TMEM lane quarter, one per 32-channel half), the N=32 modes 4.
+				// Pixel `row` is one row (kRowB bytes) of the swizzled staging tiles; 16-byte
+				// chunk c of row r lives at r*kRowB + ((c ^ sw(r)) << 4) with sw = r&7 (128B
+				// swizzle) or (r>>1)&3 (64B swizzle), so row-per-thread LDS.128 / STS.128 are
+				// bank-conflict free.  Latency is hidden by ILP inside the thread: bias stays
+				// in registers across tiles, residual and accumulator are fetched up-front,
+				// TMEM is released before the math.
+				constexpr int kTC = EPI == 3 ? 8 : 4;  // 16-byte chunks produced per thread
+				const int coff = EPI == 1 ? half * 4 : 0;  // first chunk of this thread's channels
 				if (tcount == 0 || p.n_tiles > 1) {
 #pragma unroll
-					for (int c = 0; c < kNT; ++c) bias_reg[c] = p.bias ? __ldg(p.bias + t.n0 + c) : 0.f;
+					for (int c = 0; c < 32; ++c) bias_reg[c] = p.bias ? __ldg(p.bias + t.n0 + half * 32 + c) : 0.f;
 				}
 				if (etid == 0 && tcount >= 2) {
 					// the bulk store that read staging[as] two tiles ago must have drained
 					asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
 				}
 				const uint32_t sw = EPI == 2 ? static_cast<uint32_t>((row >> 1) & 3) : static_cast<uint32_t>(row & 7);
-				uint4 res[kChunks];
+				uint4 res[4];
 				if (EPI != 3 && p.residual) {
 					mbar_wait(rfull_bar(as), aph, p.error_flag, 7);
 					const uint4 *res_row = reinterpret_cast<const uint4 *>(
 					    smem_gen + (epi_res_base - smem_base) + as * kEpiTile + row * kRowB);
 #pragma unroll
-					for (int c = 0; c < kChunks; ++c) res[c] = res_row[c ^ sw];
+					for (int c = 0; c < 4; ++c) res[c] = res_row[(coff + c) ^ sw];
 				}
 				mbar_wait(tfull_bar(as), aph, p.error_flag, 5);
 				tcgen05_fence_after();
-				uint32_t acc[kNT];
+				uint32_t acc[32];
 				const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-				                       static_cast<uint32_t>(as * p.nt);
+				                       static_cast<uint32_t>(as * p.nt + half * 32);
 				__syncwarp();
-				tmem_ld32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&acc[0]));
-				if constexpr (kNT == 64) tmem_ld32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&acc[32]));
+				tmem_ld32(taddr, acc);
 				tmem_ld_wait();
 				// TMEM and residual tile are in registers -> hand both back early
 				tcgen05_fence_before();
@@ -311,13 +319,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 					mbar_arrive(tempty_bar(as));
 					if (EPI != 3 && p.residual) mbar_arrive(rempty_bar(as));
 				}
-				epilogue_barrier();  // staging[as] free (wait_group.read above)
-				float v[kNT];
+				epilogue_barrier<EPI == 1 ? 256 : 128>();  // staging[as] free (wait_group.read above)
+				float v[32];
 #pragma unroll
-				for (int c = 0; c < kNT; ++c) v[c] = __uint_as_float(acc[c]) + bias_reg[c];
+				for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(acc[c]) + bias_reg[c];
 				if (EPI != 3 && p.residual) {
 #pragma unroll
-					for (int c = 0; c < kChunks; ++c) {
+					for (int c = 0; c < 4; ++c) {
 						const __half2 *h2 = reinterpret_cast<const __half2 *>(&res[c]);
 #pragma unroll
 						for (int e = 0; e < 4; ++e) {
@@ -329,17 +337,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 				}
 				if (p.act == ACT_RELU) {
 #pragma unroll
-					for (int c = 0; c < kNT; ++c) v[c] = fmaxf(v[c], 0.f);
+					for (int c = 0; c < 32; ++c) v[c] = fmaxf(v[c], 0.f);
 				} else if (p.act == ACT_LRELU) {
 #pragma unroll
-					for (int c = 0; c < kNT; ++c) v[c] = v[c] >= 0.f ? v[c] : v[c] * p.slope;
+					for (int c = 0; c < 32; ++c) v[c] = v[c] >= 0.f ? v[c] : v[c] * p.slope;
 				}
 				uint8_t *out_tile = smem_gen + (epi_out_base - smem_base) + as * kEpiTile;
 				if constexpr (EPI == 3) {
 					// fp32 rows: 32 floats = 8 chunks of 4
 					uint4 *out_row = reinterpret_cast<uint4 *>(out_tile + row * kRowB);
 #pragma unroll
-					for (int c = 0; c < 8; ++c) {
+					for (int c = 0; c < kTC; ++c) {
 						uint4 o;
 						o.x = __float_as_uint(v[c * 4 + 0]);
 						o.y = __float_as_uint(v[c * 4 + 1]);
@@ -348,9 +356,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 						out_row[c ^ sw] = o;
 					}
 				} else {
-					uint32_t packed[kNT / 2];
+					uint32_t packed[16];
 #pragma unroll
-					for (int c = 0; c < kNT / 2; ++c) {
+					for (int c = 0; c < 16; ++c) {
 						__half2 h = __floats2half2_rn(v[2 * c], v[2 * c + 1]);
 						packed[c] = *reinterpret_cast<uint32_t *>(&h);
 					}
@@ -358,7 +366,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 						// MaxPool2D(2): lane = (ty%4)*8 + tx, so the 2x2 window partners are
 						// lane^1 (x) and lane^8 (y); max on packed fp16 pairs is exact
 #pragma unroll
-						for (int c = 0; c < kNT / 2; ++c) {
+						for (int c = 0; c < 16; ++c) {
 							__half2 h = *reinterpret_cast<__half2 *>(&packed[c]);
 							uint32_t o1 = __shfl_xor_sync(0xffffffffu, packed[c], 1);
 							h = __hmax2(h, *reinterpret_cast<__half2 *>(&o1));
@@ -373,21 +381,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 							const uint32_t psw = EPI == 2 ? static_cast<uint32_t>((pr >> 1) & 3) : static_cast<uint32_t>(pr & 7);
 							uint4 *out_row = reinterpret_cast<uint4 *>(out_tile + pr * kRowB);
 #pragma unroll
-							for (int c = 0; c < kChunks; ++c) {
-								out_row[c ^ psw] = make_uint4(packed[c * 4], packed[c * 4 + 1], packed[c * 4 + 2], packed[c * 4 + 3]);
+							for (int c = 0; c < kTC; ++c) {
+								out_row[(coff + c) ^ psw] = make_uint4(packed[c * 4], packed[c * 4 + 1], packed[c * 4 + 2], packed[c * 4 + 3]);
 							}
 						}
 					} else {
 						uint4 *out_row = reinterpret_cast<uint4 *>(out_tile + row * kRowB);
 #pragma unroll
-						for (int c = 0; c < kChunks; ++c) {
-							out_row[c ^ sw] = make_uint4(packed[c * 4], packed[c * 4 + 1], packed[c * 4 + 2], packed[c * 4 + 3]);
+						for (int c = 0; c < kTC; ++c) {
+							out_row[(coff + c) ^ sw] = make_uint4(packed[c * 4], packed[c * 4 + 1], packed[c * 4 + 2], packed[c * 4 + 3]);
 						}
 					}
 				}
 				// make the generic-proxy smem writes visible to the TMA (async proxy)
 				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-				epilogue_barrier();
+				epilogue_barrier<EPI == 1 ? 256 : 128>();
 				if (etid == 0) {
 					// out-of-range rows/columns of ragged tiles are clipped by the TMA store
 					if (p.pool) {
@@ -744,7 +752,7 @@ cudaError_t conv_tc_launch(const ConvTcLaunch &l, int *error_flag, cudaStream_t 
 	p.error_flag = error_flag;
 	cudaLaunchConfig_t cfg{};
 	cfg.gridDim = dim3(l.grid);
-	cfg.blockDim = dim3(kThreads);
+	cfg.blockDim = dim3(p.tma_epi == 1 ? kThreadsWide : kThreads);
 	cfg.dynamicSmemBytes = l.smem_bytes;
 	cfg.stream = s;
 	cudaLaunchAttribute attr[1];

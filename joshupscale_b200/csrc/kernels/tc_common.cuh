@@ -77,12 +77,28 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, uint32_t sr
 	asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
-// the 4 epilogue warps only (threads 64..191)
-__device__ __forceinline__ void epilogue_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// the epilogue warps only (threads 64..)
+template <int kCount = 128>
+__device__ __forceinline__ void epilogue_barrier() {
+	asm volatile("bar.sync 1, %0;" ::"n"(kCount) : "memory");
+}
 
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_launch_dependents() {
 	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+// One lane of a CONVERGED warp is elected; keeping the warp converged lets the
+// compiler hold descriptors in uniform registers and issue UTCHMMA / UTMALDG
+// without the per-lane R2UR + ELECT retry loop it emits under `if (lane == 0)`.
+__device__ __forceinline__ bool elect_one_sync() {
+	uint32_t pred = 0;
+	asm volatile(
+	    "{\n\t.reg .pred p;\n\t"
+	    "elect.sync _|p, 0xffffffff;\n\t"
+	    "selp.u32 %0, 1, 0, p;\n\t}"
+	    : "=r"(pred)::"memory");
+	return pred != 0;
 }
 
 __device__ __forceinline__ void tcgen05_fence_before() {
