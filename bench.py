@@ -301,9 +301,16 @@ def run_ours(args):
         mean_usec = res_usec / grp["launches"]
         achieved = dom["flops"] / (mean_usec * 1e-6) / 1e12
         peak = peaks["tensor_sustained"]
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath) and (h, w) == (270, 480):
+            tj = json.load(open(tpath))
+            traffic = tj.get(f"batch{streams}_270x480")
         roofline = {
             "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-            "frac": achieved / peak, "traffic": None,
+            "frac": achieved / peak, "traffic": traffic,
+            "traffic_note": "dram bytes per launch from ncu --set full (profiles/ncu_traffic.json); "
+                            "algorithmic bytes per launch = %d" % int(dom["bytes"]),
             "kernel": "conv_tc_kernel<3>: ResBlock conv3x3 64->64 (generator/block_*/conv_*)",
             "launches_per_step": grp["launches"], "usec_per_launch": mean_usec,
             "usec_per_launch_isolated": sum(o["usec"] for o in res) / len(res),
