@@ -352,6 +352,10 @@ int ju_launch_conv(int impl, const void *in, const void *weights, const float *b
 			ju::ConvTcLaunch l;
 			JU_CUDA(ju::conv_tc_prepare(a, ju::conv_tc_get_variant(), &l));
 			JU_CUDA(ju::conv_tc_launch(l, nullptr, s));
+		} else if (impl == 2) {
+			ju::ConvTcLaunch l;
+			JU_CUDA(ju::conv_tc2_prepare(a, &l));
+			JU_CUDA(ju::conv_tc2_launch(l, nullptr, s));
 		} else {
 			throw std::invalid_argument("unknown conv impl");
 		}
@@ -383,7 +387,7 @@ int ju_bench_conv(int impl, int batch, int h, int w, int cin, int cout, int ksiz
 		ju::DeviceBuffer in(px * cs * 2), out(px * os * 2), res(px * os * 2), bias(cout * 4);
 		JU_CUDA(cudaMemset(in.get(), 0x2c, in.bytes()));   // fp16 0x2c2c ~ 0.065
 		JU_CUDA(cudaMemset(res.get(), 0x2c, res.bytes()));
-		const int cinp = impl == 1 ? cs : (cin + 15) / 16 * 16;
+		const int cinp = impl >= 1 ? cs : (cin + 15) / 16 * 16;
 		ju::DeviceBuffer wts(static_cast<size_t>(ksize) * ksize * cinp * cout * 2);
 		JU_CUDA(cudaMemset(wts.get(), 0x24, wts.bytes()));  // ~0.016
 		ju::ConvArgs a{};
@@ -406,9 +410,12 @@ int ju_bench_conv(int impl, int batch, int h, int w, int cin, int cout, int ksiz
 		JU_CUDA(cudaEventCreate(&e1));
 		ju::ConvTcLaunch l;
 		if (impl == 1) JU_CUDA(ju::conv_tc_prepare(a, ju::conv_tc_get_variant(), &l));
+		if (impl == 2) JU_CUDA(ju::conv_tc2_prepare(a, &l));
 		auto launch = [&] {
 			if (impl == 1) {
 				JU_CUDA(ju::conv_tc_launch(l, nullptr, nullptr));
+			} else if (impl == 2) {
+				JU_CUDA(ju::conv_tc2_launch(l, nullptr, nullptr));
 			} else {
 				JU_CUDA(ju::launch_conv_simt(a, nullptr));
 			}
@@ -433,7 +440,7 @@ int64_t ju_pack_conv_weights(int impl, const float *kernel, const float *scale, 
 		if (dst) ju::conv_simt_pack_weights(kernel, scale, ksize, cin, cin_padded, cout, static_cast<__half *>(dst));
 		return bytes;
 	}
-	if (impl == 1 && cin_padded % 64 == 0) {
+	if ((impl == 1 || impl == 2) && cin_padded % 64 == 0) {
 		auto bytes = static_cast<int64_t>(ju::conv_tc_weight_bytes(ksize, cin_padded, cout));
 		if (dst) ju::conv_tc_pack_weights(kernel, scale, ksize, cin, cin_padded, cout, static_cast<__half *>(dst));
 		return bytes;

@@ -78,6 +78,11 @@ cudaError_t conv_tc_launch(const ConvTcLaunch &l, int *error_flag, cudaStream_t 
 size_t conv_tc_weight_bytes(int ksize, int cin_padded, int cout);
 void conv_tc_pack_weights(const float *kernel, const float *scale, int ksize, int cin,
     int cin_padded, int cout, __half *dst);
+// CTA-pair (cta_group::2) variant for 3x3 64->64 fp16 layers (conv_tc2.cu);
+// weights packed by conv_tc_pack_weights
+bool conv_tc2_supported(const ConvArgs &a);
+cudaError_t conv_tc2_prepare(const ConvArgs &a, ConvTcLaunch *out);
+cudaError_t conv_tc2_launch(const ConvTcLaunch &l, int *error_flag, cudaStream_t s);
 void conv_tc_set_variant(int v);
 // -1 keeps the current value.  tma_epilogue: shared-memory epilogue with TMA
 // residual load + TMA store; pdl: programmatic dependent launch.
