@@ -40,6 +40,7 @@ constexpr uint32_t kARegion = (kABox + 1023u) & ~1023u;
 constexpr uint32_t kBSlice = 32u * 128u;              // this CTA's half of one tap's weights
 constexpr uint32_t kBBytes = 9u * kBSlice;
 constexpr uint32_t kEpiTile = 128u * 128u;
+constexpr int kResDepth = 3;  // residual tiles in flight
 
 struct Tc2Params {
 	int batch, h, w;
@@ -112,7 +113,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 	const uint32_t resb_base = smem_base + static_cast<uint32_t>(p.stages) * kARegion;
 	const uint32_t epi_out_base = resb_base + kBBytes;
 	const uint32_t epi_res_base = epi_out_base + 2u * kEpiTile;
-	const uint32_t bar_base = epi_res_base + (p.has_residual ? 2u * kEpiTile : 0u);
+	const uint32_t bar_base = epi_res_base + (p.has_residual ? kResDepth * kEpiTile : 0u);
 	auto full_bar = [&](int s) { return bar_base + 8u * s; };
 	auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
 	auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
@@ -120,7 +121,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 	const uint32_t w_bar = bar_base + 8u * (2 * kMaxStages + 4);
 	const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 5);
 	auto rfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 6 + s); };
-	auto rempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 8 + s); };
+	auto rempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 6 + kResDepth + s); };
 
 	const int warp = threadIdx.x >> 5;
 	const int lane = threadIdx.x & 31;
@@ -139,6 +140,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 		for (int s = 0; s < 2; ++s) {
 			mbar_init(tfull_bar(s), 1);    // each CTA: the leader's multicast commit
 			mbar_init(tempty_bar(s), 16);  // leader: 8 epilogue warps of each CTA
+		}
+		for (int s = 0; s < kResDepth; ++s) {
 			mbar_init(rfull_bar(s), 1);
 			mbar_init(rempty_bar(s), 8);
 		}
@@ -189,8 +192,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 			auto load_residual = [&](int tc, int pr) {
 				int b, y0, x0;
 				tile_coords(pr, b, y0, x0);
-				const int rb = tc & 1;
-				const uint32_t rph = (tc >> 1) & 1;
+				const int rb = tc % kResDepth;
+				const uint32_t rph = (tc / kResDepth) & 1;
 				mbar_wait(rempty_bar(rb), rph ^ 1u, p.error_flag, 6);
 				mbar_arrive_expect_tx(rfull_bar(rb), kEpiTile);
 				tma_load_4d(epi_res_base + rb * kEpiTile, &map_r, rfull_bar(rb), 0, x0, y0, b);
@@ -270,14 +273,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 			if (etid == 0 && it >= 2) {
 				asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
 			}
-			uint4 res[4];
-			if (p.has_residual) {
-				mbar_wait(rfull_bar(as), aph, p.error_flag, 7);
-				const uint4 *res_row = reinterpret_cast<const uint4 *>(
-				    smem_gen + (epi_res_base - smem_base) + as * kEpiTile + row * 128u);
-#pragma unroll
-				for (int c = 0; c < 4; ++c) res[c] = res_row[(coff + c) ^ sw];
-			}
 			mbar_wait(tfull_bar(as), aph, p.error_flag, 5);
 			tcgen05_fence_after();
 			uint32_t acc[32];
@@ -286,11 +281,20 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 			__syncwarp();
 			tmem_ld32(taddr, acc);
 			tmem_ld_wait();
+			// the accumulator is in registers: release TMEM to the leader's MMA warp first
 			tcgen05_fence_before();
 			__syncwarp();
-			if (lane == 0) {
-				mbar_arrive_cluster(as ? tempty_leader1 : tempty_leader0);
-				if (p.has_residual) mbar_arrive(rempty_bar(as));
+			if (lane == 0) mbar_arrive_cluster(as ? tempty_leader1 : tempty_leader0);
+			uint4 res[4];
+			if (p.has_residual) {
+				const int rb = it % kResDepth;
+				mbar_wait(rfull_bar(rb), (it / kResDepth) & 1, p.error_flag, 7);
+				const uint4 *res_row = reinterpret_cast<const uint4 *>(
+				    smem_gen + (epi_res_base - smem_base) + rb * kEpiTile + row * 128u);
+#pragma unroll
+				for (int c = 0; c < 4; ++c) res[c] = res_row[(coff + c) ^ sw];
+				__syncwarp();
+				if (lane == 0) mbar_arrive(rempty_bar(rb));
 			}
 			epilogue_barrier<256>();
 			float v[32];
@@ -388,7 +392,7 @@ cudaError_t conv_tc2_prepare(const ConvArgs &a, ConvTcLaunch *out) {
 	p.pdl = 1;
 	p.has_residual = a.residual ? 1 : 0;
 	p.bias = a.bias;
-	const uint32_t fixed = 1024u + 512u + kBBytes + (a.residual ? 4u : 2u) * kEpiTile;
+	const uint32_t fixed = 1024u + 512u + kBBytes + (a.residual ? 2u + kResDepth : 2u) * kEpiTile;
 	int stages = static_cast<int>((kSmemLimit - fixed) / kARegion);
 	if (stages > kMaxStages) stages = kMaxStages;
 	if (stages < 2) return cudaErrorInvalidValue;
