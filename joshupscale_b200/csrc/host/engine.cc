@@ -41,6 +41,7 @@ Engine::Engine(const ModelFile &model, int device, int batch)
 	if (const char *v = std::getenv("JU_TC_TMA_EPILOGUE")) conv_tc_set_flags(std::atoi(v), -1);
 	if (const char *v = std::getenv("JU_TC_PDL")) conv_tc_set_flags(-1, std::atoi(v));
 	m_UseGraph = envInt("JU_NO_GRAPH", 0) == 0;
+	m_Conv2Cta = envInt("JU_CONV_2CTA", 0) != 0;
 	JU_CUDA(cudaStreamCreateWithFlags(&m_Stream, cudaStreamNonBlocking));
 	try {
 		buildLayers(model);
@@ -263,6 +264,15 @@ Op Engine::convOp(ConvLayer *L, const __half *in, int cinStride, const __half *r
 		ConvArgs t = a;
 		t.weights = L->wTc.get();
 		t.cin = pad64(L->cinReal);
+		if (t.cin <= cinStride && m_Conv2Cta && conv_tc2_supported(t)) {
+			// experimental CTA-pair kernel (JU_CONV_2CTA=1): only faster at batch 1, see DESIGN.md 6
+			ConvTcLaunch launch;
+			checkCuda(conv_tc2_prepare(t, &launch), "conv_tc2_prepare");
+			int *err = m_TcError.as<int>();
+			op.run = [launch, err](cudaStream_t s) { return conv_tc2_launch(launch, err, s); };
+			++m_TcOps;
+			return op;
+		}
 		if (t.cin <= cinStride && conv_tc_supported(t)) {
 			ConvTcLaunch launch;
 			cudaError_t prep = conv_tc_prepare(t, conv_tc_get_variant(), &launch);

@@ -92,6 +92,7 @@ private:
 	int m_Batch = 1;
 	int m_ConvImpl = 0;
 	bool m_UseGraph = true;
+	bool m_Conv2Cta = false;
 	int m_Parity = 0;
 	cudaStream_t m_Stream = nullptr;
 	cudaGraphExec_t m_GraphExec[2] = {nullptr, nullptr};
