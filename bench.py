@@ -297,10 +297,13 @@ def run_ours(args):
         grp = groups["resblocks"]
         res_usec = grp["usec"]
         frame_usec = sum(g["usec"] for g in groups.values())
-        dom = res[len(res) // 2]
-        mean_usec = res_usec / grp["launches"]
-        achieved = dom["flops"] / (mean_usec * 1e-6) / 1e12
+        layers = grp["launches"]                      # ResBlock conv layers per frame
+        flops_per_layer = grp["flops"] / layers       # 9.555 GFLOP at PSP batch 1
+        bytes_per_layer = grp["bytes"] / layers
+        mean_usec = res_usec / layers
+        achieved = grp["flops"] / (res_usec * 1e-6) / 1e12
         peak = peaks["tensor_sustained"]
+        persistent = len(res) == 1 and layers > 1
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath) and (h, w) == (270, 480):
@@ -309,12 +312,13 @@ def run_ours(args):
         roofline = {
             "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
             "frac": achieved / peak, "traffic": traffic,
-            "traffic_note": "dram bytes per launch from ncu --set full (profiles/ncu_traffic.json); "
-                            "algorithmic bytes per launch = %d" % int(dom["bytes"]),
-            "kernel": "conv_tc_kernel<3>: ResBlock conv3x3 64->64 (generator/block_*/conv_*)",
-            "launches_per_step": grp["launches"], "usec_per_launch": mean_usec,
-            "usec_per_launch_isolated": sum(o["usec"] for o in res) / len(res),
-            "flops_per_launch": dom["flops"], "share_of_step": res_usec / frame_usec,
+            "traffic_note": "dram bytes per layer from ncu --set full of the per-layer kernel (profiles/ncu_traffic.json); "
+                            "algorithmic bytes per layer = %d" % int(bytes_per_layer),
+            "kernel": ("trunk_tc_kernel: all ResBlock conv3x3 64->64 layers in one persistent launch"
+                       if persistent else "conv_tc_kernel<3,1>: ResBlock conv3x3 64->64 (generator/block_*/conv_*)"),
+            "layers_per_step": layers, "kernel_launches_per_step": len(res), "usec_per_layer": mean_usec,
+            "usec_per_launch": res_usec / len(res),
+            "flops_per_layer": flops_per_layer, "share_of_step": res_usec / frame_usec,
             "frac_of_burst_peak": achieved / peaks["tensor_burst"],
             "peak_source": f"{peaks['source']} bf16 dense, sustained (burst {peaks['tensor_burst']})",
         }

@@ -83,7 +83,7 @@ typedef struct ju_op_time {
 	double flops;      /* algorithmic FLOPs per launch (0 if bandwidth-bound) */
 	double bytes;      /* algorithmic bytes per launch */
 	int32_t tensor_bound;
-	int32_t reserved;  /* launches covered: 1 for a kernel, N for a "group:<label>" entry */
+	int32_t reserved;  /* network layers covered (1 per kernel; the persistent trunk and "group:" entries cover many) */
 } ju_op_time;
 
 typedef void (*ju_log_fn)(const char *tag, int level, const char *message, void *user);

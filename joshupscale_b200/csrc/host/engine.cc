@@ -426,11 +426,61 @@ void Engine::buildPlan(int parity) {
 	__half *t0 = m_Trunk[0].as<__half>(), *t1 = m_Trunk[1].as<__half>(), *t2 = m_Trunk[2].as<__half>();
 	plan.push_back(convOp(layer("generator/conv_1"), m_GenIn.as<__half>(), 64, nullptr, t0, gs, H, W, false));
 	__half *cur = t0, *tmp = t1, *nxt = t2;
-	for (int i = 0; i < s.genBlocks; ++i) {
-		std::string p = "generator/block_" + std::to_string(i + 1);
-		plan.push_back(convOp(layer(p + "/conv_1"), cur, gs, nullptr, tmp, gs, H, W, false));
-		plan.push_back(convOp(layer(p + "/conv_2"), tmp, gs, cur, nxt, gs, H, W, false));
-		std::swap(cur, nxt);
+	const bool fusedTrunk = m_ConvImpl == 1 && s.genFilters == 64 && s.genBlocks > 0 && gs % 64 == 0 &&
+	                        envInt("JU_FUSED_TRUNK", 1) != 0 && !m_Conv2Cta;
+	if (fusedTrunk) {
+		// all 2 x genBlocks ResBlock convolutions in ONE persistent launch (trunk_tc.cu)
+		const int nLayers = 2 * s.genBlocks;
+		if (!m_TrunkWeights.get()) {
+			const std::size_t per = conv_tc_weight_bytes(3, 64, 64);
+			m_TrunkWeights = DeviceBuffer(per * nLayers);
+			m_TrunkBias = DeviceBuffer(sizeof(float) * 64 * nLayers);
+			m_TrunkCounter = DeviceBuffer(sizeof(unsigned int));
+			for (int l = 0; l < nLayers; ++l) {
+				ConvLayer *L = layer("generator/block_" + std::to_string(l / 2 + 1) + "/conv_" + std::to_string(l % 2 + 1));
+				if (!L->wTc.get() || L->cout != 64 || L->cinReal != 64 || L->ksize != 3) {
+					throw ModelException("unexpected ResBlock layer shape");
+				}
+				JU_CUDA(cudaMemcpy(m_TrunkWeights.as<char>() + per * l, L->wTc.get(), per, cudaMemcpyDeviceToDevice));
+				JU_CUDA(cudaMemcpy(m_TrunkBias.as<float>() + 64 * l, L->bias.get(), 64 * sizeof(float),
+				    cudaMemcpyDeviceToDevice));
+			}
+		}
+		ConvLayer *first = layer("generator/block_1/conv_1");
+		TrunkArgs ta{};
+		ta.buffers[0] = t0;
+		ta.buffers[1] = t1;
+		ta.buffers[2] = t2;
+		ta.cstride = gs;
+		ta.weights = m_TrunkWeights.get();
+		ta.bias = m_TrunkBias.as<float>();
+		ta.sync_counter = m_TrunkCounter.as<unsigned int>();
+		ta.batch = B;
+		ta.h = H;
+		ta.w = W;
+		ta.n_layers = nLayers;
+		ta.act = first->act;
+		ta.slope = first->slope;
+		TrunkTcLaunch launch;
+		checkCuda(trunk_tc_prepare(ta, &launch), "trunk_tc_prepare");
+		Op op;
+		op.name = "generator/block_*(persistent)";
+		op.tensorBound = true;
+		op.layers = nLayers;
+		op.flops = 2.0 * B * H * W * 9.0 * 64 * 64 * nLayers;
+		op.bytes = static_cast<double>(B) * H * W * 64 * 2.0 * (2.0 * nLayers + 0.5 * nLayers);
+		int *err = m_TcError.as<int>();
+		op.run = [launch, err](cudaStream_t st) { return trunk_tc_launch(launch, err, st); };
+		plan.push_back(std::move(op));
+		++m_TcOps;
+		cur = trunk_output_buffer(nLayers) == 0 ? t0 : t2;
+	} else {
+		for (int i = 0; i < s.genBlocks; ++i) {
+			std::string p = "generator/block_" + std::to_string(i + 1);
+			plan.push_back(convOp(layer(p + "/conv_1"), cur, gs, nullptr, tmp, gs, H, W, false));
+			plan.push_back(convOp(layer(p + "/conv_2"), tmp, gs, cur, nxt, gs, H, W, false));
+			std::swap(cur, nxt);
+		}
 	}
 	if (parity == 0) {
 		registerTensor("trunk", cur, nullptr, 1,
@@ -681,7 +731,7 @@ std::vector<ju_op_time> Engine::profileOps(int iters) {
 		o.flops = plan[i].flops;
 		o.bytes = plan[i].bytes;
 		o.tensor_bound = plan[i].tensorBound ? 1 : 0;
-		o.reserved = 1;
+		o.reserved = plan[i].layers;
 	}
 	// Second pass: events only at group boundaries, so kernels inside a group
 	// run back to back exactly as in the replayed graph (programmatic dependent
@@ -753,7 +803,8 @@ std::vector<ju_op_time> Engine::profileOps(int iters) {
 			o.bytes += plan[i].bytes;
 			o.tensor_bound |= plan[i].tensorBound ? 1 : 0;
 		}
-		o.reserved = static_cast<int>(firstOp[g + 1] - firstOp[g]);
+		o.reserved = 0;
+		for (std::size_t i = firstOp[g]; i < firstOp[g + 1]; ++i) o.reserved += plan[i].layers;
 		result.push_back(o);
 	}
 	for (auto &e : ev) cudaEventDestroy(e);

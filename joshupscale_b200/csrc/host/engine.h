@@ -43,6 +43,7 @@ struct Op {
 	double flops = 0;  // algorithmic (true channel counts)
 	double bytes = 0;  // algorithmic bytes moved
 	bool tensorBound = false;
+	int layers = 1;  // network layers covered by this launch (the persistent trunk covers many)
 };
 
 struct NamedTensor {
@@ -101,6 +102,7 @@ private:
 	DeviceBuffer m_IoDev;
 	DeviceBuffer m_TcError;
 	DeviceBuffer m_Brightness;
+	DeviceBuffer m_TrunkWeights, m_TrunkBias, m_TrunkCounter;
 	int m_TcOps = 0;
 	DeviceBuffer m_InStage, m_OutStage;
 	std::vector<ju_image> m_LastOutputs;

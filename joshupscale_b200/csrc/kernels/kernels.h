@@ -118,6 +118,30 @@ struct TailTcLaunch {
 cudaError_t tail_tc_prepare(const TailArgs &a, TailTcLaunch *out);
 cudaError_t tail_tc_launch(const TailTcLaunch &l, int *error_flag, cudaStream_t s);
 
+// ---- persistent ResBlock trunk (trunk_tc.cu): all 3x3 64->64 layers in one launch
+struct TrunkArgs {
+	void *buffers[3];        // T0 (input of the first block), T1, T2: [batch, h, w, cstride] fp16
+	int cstride;
+	const void *weights;     // n_layers x conv_tc_pack_weights(3, 64, 64, 64), concatenated
+	const float *bias;       // [n_layers][64]
+	unsigned int *sync_counter;  // one zero-initialised device word per engine
+	int batch, h, w;
+	int n_layers;            // 2 x ResBlocks
+	int act;
+	float slope;
+};
+struct TrunkTcLaunch {
+	alignas(64) unsigned char maps[7 * 128];
+	alignas(8) unsigned char params[128];
+	int grid;
+	unsigned int smem_bytes;
+	unsigned int *sync_counter;
+};
+cudaError_t trunk_tc_prepare(const TrunkArgs &a, TrunkTcLaunch *out);
+cudaError_t trunk_tc_launch(const TrunkTcLaunch &l, int *error_flag, cudaStream_t s);
+// index (0 or 2) of the buffer holding the trunk output after n_layers
+inline int trunk_output_buffer(int n_layers) { return ((n_layers / 2) & 1) ? 2 : 0; }
+
 cudaError_t launch_maxpool2(const __half *in, __half *out, int batch, int h, int w, int c, cudaStream_t s);
 cudaError_t launch_upscale2(const __half *in, __half *out, int batch, int h, int w, int c, cudaStream_t s);
 

@@ -170,3 +170,25 @@ def test_conv_tc_fused_maxpool(b, h, w, cin, cout):
     want = og.max_pool2(_t(full.astype(np.float32))).numpy().astype(np.float16)
     assert pooled.shape == (b, h // 2, w // 2, cout)
     np.testing.assert_array_equal(pooled.view(np.uint16), want.view(np.uint16))
+
+
+@pytest.mark.parametrize("preset,batch", [("small", 1), ("small", 3), ("psp_fast", 1)])
+def test_persistent_trunk_bit_identical_to_per_layer_launches(tmp_path, preset, batch):
+    """The persistent ResBlock trunk (one launch, grid barriers between layers) performs the
+    same arithmetic as one conv_tc launch per layer: outputs must match bit for bit."""
+    cfg, w, path = make_model(tmp_path, preset)
+    frames = [synthetic.frames(cfg.frame_height, cfg.frame_width, 3, stream_id=s) for s in range(batch)]
+    outs = {}
+    for fused in ("1", "0"):
+        os.environ["JU_FUSED_TRUNK"] = fused
+        try:
+            with jrt.Runtime(path, 0, batch) as rt:
+                res = []
+                for t in range(3):
+                    res.append(np.stack(rt.process_batch([f[t] for f in frames])))
+                outs[fused] = np.stack(res)
+                if fused == "1":
+                    assert rt.info.kernels_per_frame < 30 + 0 * cfg.gen_blocks
+        finally:
+            os.environ.pop("JU_FUSED_TRUNK", None)
+    np.testing.assert_array_equal(outs["1"], outs["0"])
