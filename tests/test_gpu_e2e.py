@@ -211,3 +211,70 @@ def test_cxx_api_like_the_plugins(tmp_path):
     assert "ModelException" in r.stdout and "model.jup" in r.stdout
     got = np.fromfile(fout, np.uint8).reshape(want.shape)
     np.testing.assert_array_equal(got, want)
+
+
+def test_long_sequence_does_not_drift(tmp_path):
+    """40 recurrent frames: the fp16 engine tracks the fp32 graph without accumulating error."""
+    cfg, w, path = make_model(tmp_path, "small")
+    frames = synthetic.frames(cfg.frame_height, cfg.frame_width, 40)
+    got = _run_gpu(path, frames)
+    ref, _ = og.Graph(cfg, w, "fp32").run(frames)
+    psnrs = [u8_stats(got[t, ..., :3], ref[t, ..., :3]) for t in range(40)]
+    assert max(p[0] for p in psnrs) <= MAX_ABS_FP32
+    assert min(p[2] for p in psnrs[30:]) >= MIN_PSNR_DB
+    assert min(p[2] for p in psnrs[30:]) > min(p[2] for p in psnrs[:10]) - 3.0
+
+
+def test_ps2_size_and_fast_model(tmp_path):
+    """BASELINE configs 2 and 4: PS2 frame size (360x480 -> 1440x1920) and the fast generator."""
+    import dataclasses
+    from joshupscale_b200 import config as jcfg
+    cfg = dataclasses.replace(jcfg.preset("ps2_fast"), gen_blocks=2)
+    cfg, w, path = make_model(tmp_path, cfg)
+    frames = synthetic.frames(360, 480, 3)
+    got = _run_gpu(path, frames)
+    assert got.shape == (3, 1440, 1920, 4)
+    ref, _ = og.Graph(cfg, w, "fp32").run(frames)
+    for t in range(3):
+        m, _, p = u8_stats(got[t, ..., :3], ref[t, ..., :3])
+        assert m <= MAX_ABS_FP32 and p >= MIN_PSNR_DB
+
+
+def test_two_runtimes_interleaved_and_threaded(tmp_path):
+    """Different models in one process (the OBS plugin switches presets; config 5 mixes
+    quality and fast streams on one GPU): instances must not share mutable state."""
+    import threading
+    cfg_a, w_a, path_a = make_model(tmp_path, "small", seed=1)
+    cfg_b, w_b, path_b = make_model(tmp_path, "small_resnet", seed=2)
+    fa = synthetic.frames(cfg_a.frame_height, cfg_a.frame_width, 4, stream_id=1)
+    fb = synthetic.frames(cfg_b.frame_height, cfg_b.frame_width, 4, stream_id=2)
+    want_a, want_b = _run_gpu(path_a, fa), _run_gpu(path_b, fb)
+    with jrt.Runtime(path_a) as ra, jrt.Runtime(path_b) as rb:
+        for t in range(2):  # interleaved on one thread
+            np.testing.assert_array_equal(ra.process(fa[t]), want_a[t])
+            np.testing.assert_array_equal(rb.process(fb[t]), want_b[t])
+        results = {}
+
+        def worker(name, rt, frames):
+            results[name] = [rt.process(f) for f in frames[2:]]
+
+        ths = [threading.Thread(target=worker, args=("a", ra, fa)), threading.Thread(target=worker, args=("b", rb, fb))]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+        for t in range(2):
+            np.testing.assert_array_equal(results["a"][t], want_a[2 + t])
+            np.testing.assert_array_equal(results["b"][t], want_b[2 + t])
+
+
+def test_full_size_batch_equals_single(tmp_path):
+    """PSP fast at full size, 3 streams batched == each stream alone (persistent trunk, batch > 1)."""
+    cfg, w, path = make_model(tmp_path, "psp_fast")
+    streams = [synthetic.frames(270, 480, 2, stream_id=s) for s in range(3)]
+    singles = [_run_gpu(path, s) for s in streams]
+    with jrt.Runtime(path, 0, 3) as rt:
+        for t in range(2):
+            outs = rt.process_batch([s[t] for s in streams])
+            for s in range(3):
+                np.testing.assert_array_equal(outs[s], singles[s][t])
