@@ -435,7 +435,8 @@ void Engine::buildPlan(int parity) {
 			const std::size_t per = conv_tc_weight_bytes(3, 64, 64);
 			m_TrunkWeights = DeviceBuffer(per * nLayers);
 			m_TrunkBias = DeviceBuffer(sizeof(float) * 64 * nLayers);
-			m_TrunkCounter = DeviceBuffer(sizeof(unsigned int));
+			m_TrunkCounter = DeviceBuffer(sizeof(unsigned int) * 2);
+			m_TrunkFlags = DeviceBuffer(sizeof(unsigned int) * static_cast<std::size_t>(B) * ((H + 15) / 16) * ((W + 7) / 8));
 			for (int l = 0; l < nLayers; ++l) {
 				ConvLayer *L = layer("generator/block_" + std::to_string(l / 2 + 1) + "/conv_" + std::to_string(l % 2 + 1));
 				if (!L->wTc.get() || L->cout != 64 || L->cinReal != 64 || L->ksize != 3) {
@@ -455,6 +456,7 @@ void Engine::buildPlan(int parity) {
 		ta.weights = m_TrunkWeights.get();
 		ta.bias = m_TrunkBias.as<float>();
 		ta.sync_counter = m_TrunkCounter.as<unsigned int>();
+		ta.flags = m_TrunkFlags.as<unsigned int>();
 		ta.batch = B;
 		ta.h = H;
 		ta.w = W;
@@ -462,7 +464,9 @@ void Engine::buildPlan(int parity) {
 		ta.act = first->act;
 		ta.slope = first->slope;
 		TrunkTcLaunch launch;
-		checkCuda(trunk_tc_prepare(ta, &launch), "trunk_tc_prepare");
+		// JU_TRUNK_SYNC: 1 = per-tile dataflow flags (trunk_df_tc.cu), 0 = grid barrier per layer (trunk_tc.cu)
+		const bool dataflow = envInt("JU_TRUNK_SYNC", 0) != 0;
+		checkCuda(dataflow ? trunk_df_tc_prepare(ta, &launch) : trunk_tc_prepare(ta, &launch), "trunk_tc_prepare");
 		Op op;
 		op.name = "generator/block_*(persistent)";
 		op.tensorBound = true;
@@ -470,7 +474,11 @@ void Engine::buildPlan(int parity) {
 		op.flops = 2.0 * B * H * W * 9.0 * 64 * 64 * nLayers;
 		op.bytes = static_cast<double>(B) * H * W * 64 * 2.0 * (2.0 * nLayers + 0.5 * nLayers);
 		int *err = m_TcError.as<int>();
-		op.run = [launch, err](cudaStream_t st) { return trunk_tc_launch(launch, err, st); };
+		if (dataflow) {
+			op.run = [launch, err](cudaStream_t st) { return trunk_df_tc_launch(launch, err, st); };
+		} else {
+			op.run = [launch, err](cudaStream_t st) { return trunk_tc_launch(launch, err, st); };
+		}
 		plan.push_back(std::move(op));
 		++m_TcOps;
 		cur = trunk_output_buffer(nLayers) == 0 ? t0 : t2;

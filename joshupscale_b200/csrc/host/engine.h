@@ -102,7 +102,7 @@ private:
 	DeviceBuffer m_IoDev;
 	DeviceBuffer m_TcError;
 	DeviceBuffer m_Brightness;
-	DeviceBuffer m_TrunkWeights, m_TrunkBias, m_TrunkCounter;
+	DeviceBuffer m_TrunkWeights, m_TrunkBias, m_TrunkCounter, m_TrunkFlags;
 	int m_TcOps = 0;
 	DeviceBuffer m_InStage, m_OutStage;
 	std::vector<ju_image> m_LastOutputs;

@@ -124,7 +124,8 @@ struct TrunkArgs {
 	int cstride;
 	const void *weights;     // n_layers x conv_tc_pack_weights(3, 64, 64, 64), concatenated
 	const float *bias;       // [n_layers][64]
-	unsigned int *sync_counter;  // one zero-initialised device word per engine
+	unsigned int *sync_counter;  // two zero-initialised device words per engine (counter, epoch)
+	unsigned int *flags;         // dataflow version: one zero-initialised word per 16x8 pixel tile
 	int batch, h, w;
 	int n_layers;            // 2 x ResBlocks
 	int act;
@@ -139,6 +140,9 @@ struct TrunkTcLaunch {
 };
 cudaError_t trunk_tc_prepare(const TrunkArgs &a, TrunkTcLaunch *out);
 cudaError_t trunk_tc_launch(const TrunkTcLaunch &l, int *error_flag, cudaStream_t s);
+// dataflow version (trunk_df_tc.cu): per-tile completion flags instead of the grid barrier
+cudaError_t trunk_df_tc_prepare(const TrunkArgs &a, TrunkTcLaunch *out);
+cudaError_t trunk_df_tc_launch(const TrunkTcLaunch &l, int *error_flag, cudaStream_t s);
 // index (0 or 2) of the buffer holding the trunk output after n_layers
 inline int trunk_output_buffer(int n_layers) { return ((n_layers / 2) & 1) ? 2 : 0; }
 
