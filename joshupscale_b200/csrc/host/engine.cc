@@ -436,7 +436,7 @@ void Engine::buildPlan(int parity) {
 			m_TrunkWeights = DeviceBuffer(per * nLayers);
 			m_TrunkBias = DeviceBuffer(sizeof(float) * 64 * nLayers);
 			m_TrunkCounter = DeviceBuffer(sizeof(unsigned int) * 2);
-			m_TrunkFlags = DeviceBuffer(sizeof(unsigned int) * static_cast<std::size_t>(B) * ((H + 15) / 16) * ((W + 7) / 8));
+			m_TrunkFlags = DeviceBuffer(sizeof(unsigned int) * static_cast<std::size_t>(nLayers) * B * ((H + 15) / 16) * ((W + 7) / 8));
 			for (int l = 0; l < nLayers; ++l) {
 				ConvLayer *L = layer("generator/block_" + std::to_string(l / 2 + 1) + "/conv_" + std::to_string(l % 2 + 1));
 				if (!L->wTc.get() || L->cout != 64 || L->cinReal != 64 || L->ksize != 3) {

@@ -125,7 +125,7 @@ struct TrunkArgs {
 	const void *weights;     // n_layers x conv_tc_pack_weights(3, 64, 64, 64), concatenated
 	const float *bias;       // [n_layers][64]
 	unsigned int *sync_counter;  // two zero-initialised device words per engine (counter, epoch)
-	unsigned int *flags;         // dataflow version: one zero-initialised word per 16x8 pixel tile
+	unsigned int *flags;         // dataflow version: zero-initialised [n_layers][waves] counters (>= n_layers * tiles words)
 	int batch, h, w;
 	int n_layers;            // 2 x ResBlocks
 	int act;

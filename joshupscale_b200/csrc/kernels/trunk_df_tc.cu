@@ -2,14 +2,15 @@
 // layers of the generator's residual stack - scripts/training/models.py:193-254,
 // 544-550 - in one launch), but without any grid-wide barrier.
 //
-// A tile of layer l only needs the 3x3 tile neighbourhood of layer l-1, so each
-// stored tile publishes a generation number in a per-tile flag word
-// (st.release.gpu after the TMA store has completed) and the TMA producer polls
-// the <= 9 neighbour flags (one lane each, ld.acquire.gpu) before it requests a
-// halo.  With the static tile->CTA striding all CTAs advance in waves, the
-// neighbours of wave k were stored a full layer earlier, so in steady state no
-// CTA ever waits at a layer boundary and the producer prefetches halos of layer
-// l+1 while the MMAs of layer l are still running.
+// A tile of layer l only needs the 3x3 tile neighbourhood of layer l-1.  With the
+// static tile->CTA striding (tile = cta + k*grid) all CTAs advance in waves k, and
+// the neighbours of a wave-k tile lie in waves k-1..k+1, so the dependency is kept
+// per (layer, wave): every completed TMA store bumps a counter (release), and the
+// TMA producer needs counter[l-1][k+1] to be full (acquire) before it requests a
+// halo of layer l, wave k - one cached poll per wave instead of a grid barrier.
+// Wave 0 of layer l+1 only needs waves 0..1 of layer l, which were stored almost a
+// whole layer earlier: in steady state no CTA waits at a layer boundary and the
+// producer prefetches halos of layer l+1 while the MMAs of layer l still run.
 //
 // The resident weights are swapped tap by tap: on a CTA's last tile of layer l the
 // MMA warp commits one barrier per tap, a dedicated loader warp refills that tap's
@@ -20,9 +21,9 @@
 // layers after it was read, and the read-after-write chain of the writer
 // (neighbours of neighbours) covers every reader of the old contents.
 //
-// Generation numbers are epoch*n_layers + layer + 1 with a per-launch epoch kept in
-// global memory (advanced by the last CTA to finish), compared wrap-safe, so the
-// captured CUDA graph replays without any reset node.
+// Counters are never reset: launch number `epoch` (kept in global memory, advanced
+// by the last CTA to finish) expects (epoch+1) * tiles_in_wave, compared wrap-safe,
+// so the captured CUDA graph replays without any memset node.
 #include <cstring>
 
 #include "kernels.h"
@@ -54,7 +55,7 @@ struct TrunkParams {
 	int pdl;
 	const float *bias;            // [n_layers][64]
 	unsigned int *sync_counter;   // [0] finished-CTA counter, [1] launch epoch
-	unsigned int *flags;          // [total_tiles] last stored generation per tile
+	unsigned int *flags;          // [n_layers][n_waves] stored-tile counters, never reset
 	int *error_flag;
 };
 
@@ -138,17 +139,17 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 
 	// launch epoch: identical for every CTA of this launch (advanced by the last CTA to finish)
 	const unsigned int epoch = *reinterpret_cast<volatile unsigned int *>(p.sync_counter + 1);
-	const unsigned int gen_base = epoch * static_cast<unsigned int>(p.n_layers);
+	const int n_waves = (p.total_tiles + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+	// the 3x3 tile neighbourhood spans tile indices t +- (tiles_x + 1): that many waves ahead must be complete
+	const int wave_reach = (p.tiles_x + 1 + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
 
 	if (warp == 0) {
 		// ===================== TMA producer (warp converged; lanes 0..8 poll neighbour flags) =====
 		if (p.pdl) grid_dependency_wait();
-		const int dy = lane / 3 - 1, dx = lane % 3 - 1;  // neighbour handled by this lane (lanes 0..8)
 		int it = 0, tcount = 0;
 		for (int l = 0; l < p.n_layers; ++l) {
 			const CUtensorMap *min = &maps.in[layer_in(l)];
 			const int r = layer_res(l);
-			const unsigned int need = gen_base + static_cast<unsigned int>(l);  // generation of layer l-1
 			auto load_residual = [&](int tc, int tile) {
 				int b, y0, x0;
 				decode(tile, b, y0, x0);
@@ -162,31 +163,41 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 				__syncwarp();
 			};
 			int prev_tile = -1;
+			int known = -1;  // highest wave of layer l-1 known to be completely stored
 			for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
 				int b, y0, x0;
 				decode(tile, b, y0, x0);
 				const int s = it % p.stages;
 				const uint32_t ph = (it / p.stages) & 1;
 				mbar_wait(empty_bar(s), ph ^ 1u, p.error_flag, 1);
+				bool polled = false;
 				if (l > 0) {
-					// wait until the 3x3 tile neighbourhood of layer l-1 has been stored
-					const int tx = x0 / kTileW + dx, ty = y0 / kTileH + dy;
-					const bool check = lane < 9 && tx >= 0 && tx < p.tiles_x && ty >= 0 && ty < p.tiles_y;
-					const unsigned int *flag = p.flags + (static_cast<size_t>(b) * p.tiles_y + (check ? ty : 0)) * p.tiles_x + (check ? tx : 0);
-					unsigned int spins = 0;
-					while (true) {
-						const bool ok = !check || static_cast<int>(ld_acquire_gpu(flag) - need) >= 0;
-						if (__all_sync(0xffffffffu, ok)) break;
-						__nanosleep(32);
-						if (++spins > (1u << 24)) {
-							if (p.error_flag) atomicExch(p.error_flag, 8);
-							__trap();
+					// waves <= k+1 of layer l-1 must be completely stored (covers the 3x3 neighbourhood)
+					const int k = (tile - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x);
+					const int needw = k + wave_reach < n_waves ? k + wave_reach : n_waves - 1;
+					while (known < needw) {
+						const int wv = known + 1;
+						const int cnt = wv + 1 < n_waves ? static_cast<int>(gridDim.x)
+						                                 : p.total_tiles - wv * static_cast<int>(gridDim.x);
+						const unsigned int target = (epoch + 1u) * static_cast<unsigned int>(cnt);
+						const unsigned int *ctr = p.flags + (l - 1) * n_waves + wv;
+						unsigned int spins = 0;
+						while (static_cast<int>(ld_acquire_gpu(ctr) - target) < 0) {
+							__nanosleep(32);
+							if (++spins > (1u << 24)) {
+								if (p.error_flag) atomicExch(p.error_flag, 8);
+								__trap();
+							}
 						}
+						known = wv;
+						polled = true;
 					}
 				}
 				if (lane == 0) {
-					// order the async-proxy (TMA) read below after the acquire loads above
-					asm volatile("fence.proxy.async;" ::: "memory");
+					if (polled) {
+						// order the async-proxy (TMA) reads below after the acquire loads above
+						asm volatile("fence.proxy.async;" ::: "memory");
+					}
 					mbar_arrive_expect_tx(full_bar(s), kABox);
 					tma_load_4d(smem_base + s * kARegion, min, full_bar(s), 0, x0 - 1, y0 - 1, b);
 				}
@@ -261,13 +272,12 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 		const int coff = half * 4;
 		if (p.pdl) grid_dependency_wait();
 		int it = 0, rcount = 0;
-		int pending_tile = -1;             // stored, flag not yet published (store thread only)
-		unsigned int pending_gen = 0;
-		auto publish = [&](int tile, unsigned int gen) {
-			// the bulk store of `tile` has completed: make it visible GPU-wide, then raise its flag
+		int pending = -1;  // counter index of a stored tile that is not yet published (store thread only)
+		auto publish = [&](int idx) {
+			// the bulk store has completed: make it visible GPU-wide, then count the tile
 			asm volatile("fence.proxy.async;" ::: "memory");
 			__threadfence();
-			asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.flags + tile), "r"(gen) : "memory");
+			asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.flags + idx) : "memory");
 		};
 		for (int l = 0; l < p.n_layers; ++l) {
 			float bias_reg[32];
@@ -347,18 +357,24 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 					tma_store_4d(mout, epi_out_base + as * kEpiTile, 0, x0, y0, b);
 					// flags lag one tile behind the stores, so this thread never waits on a store it
 					// has just issued (consumers need tiles that were stored a whole layer earlier)
-					if (pending_tile >= 0) {
+					if (pending >= 0) {
 						asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
-						publish(pending_tile, pending_gen);
+						publish(pending);
 					}
-					pending_tile = tile;
-					pending_gen = gen_base + static_cast<unsigned int>(l) + 1u;
+					pending = l * n_waves + (tile - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x);
 				}
+			}
+			// with too few waves the next layer's first wave depends on this layer's last one:
+			// publish it now instead of lazily (costs one store-completion wait per layer)
+			if (etid == 0 && n_waves < wave_reach + 2 && pending >= 0) {
+				asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+				publish(pending);
+				pending = -1;
 			}
 		}
 		if (etid == 0) {
 			asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-			if (pending_tile >= 0) publish(pending_tile, pending_gen);
+			if (pending >= 0) publish(pending);
 			__threadfence();
 			// the last CTA to finish advances the epoch for the next launch
 			const unsigned int old = atomicAdd(p.sync_counter, 1u);
