@@ -36,7 +36,7 @@ namespace {
 using namespace tc;
 
 constexpr int kTileH = 16, kTileW = 8;
-constexpr int kThreadsT = 352;  // producer warp, MMA warp, 8 epilogue warps, weight-loader warp
+constexpr int kThreadsT = 384;  // producer, MMA, 8 epilogue warps, weight-loader warp, store/publish warp
 constexpr int kMaxStages = 8;
 constexpr uint32_t kSmemLimit = 227 * 1024;
 constexpr uint32_t kABox = 18u * 10u * 128u;
@@ -89,6 +89,8 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 	auto rempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 8 + s); };
 	auto wfull_tap = [&](int t) { return bar_base + 8u * (2 * kMaxStages + 10 + t); };
 	auto wempty_tap = [&](int t) { return bar_base + 8u * (2 * kMaxStages + 19 + t); };
+	auto sready_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 28 + s); };  // staging tile written
+	auto sfree_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 30 + s); };   // staging tile read by the TMA store
 
 	const int warp = threadIdx.x >> 5;
 	const int lane = threadIdx.x & 31;
@@ -104,6 +106,8 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 			mbar_init(tempty_bar(s), 8);
 			mbar_init(rfull_bar(s), 1);
 			mbar_init(rempty_bar(s), 8);
+			mbar_init(sready_bar(s), 8);
+			mbar_init(sfree_bar(s), 1);
 		}
 		for (int t = 0; t < 9; ++t) {
 			mbar_init(wfull_tap(t), 1);
@@ -218,6 +222,56 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 				}
 			}
 		}
+	} else if (warp == 11) {
+		// ===================== store + publish warp =====================
+		// Issues the TMA store of every finished tile and publishes its completion, so no
+		// epilogue warp ever waits on a store or on a GPU-scope fence.
+		if (lane == 0) {
+			if (p.pdl) grid_dependency_wait();
+			int it = 0;
+			int pending = -1;  // counter index of a stored tile that is not yet published
+			auto publish = [&](int idx) {
+				// the bulk store has completed: make it visible GPU-wide, then count the tile
+				asm volatile("fence.proxy.async;" ::: "memory");
+				__threadfence();
+				asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.flags + idx) : "memory");
+			};
+			for (int l = 0; l < p.n_layers; ++l) {
+				const CUtensorMap *mout = &maps.tile[layer_out(l)];
+				for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+					int b, y0, x0;
+					decode(tile, b, y0, x0);
+					const int as = it & 1;
+					const uint32_t aph = (it >> 1) & 1;
+					mbar_wait(sready_bar(as), aph, p.error_flag, 10);
+					tma_store_4d(mout, epi_out_base + as * kEpiTile, 0, x0, y0, b);
+					asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem tile consumed
+					mbar_arrive(sfree_bar(as));
+					// counters lag one tile behind the stores: the store waited for here was issued a
+					// whole tile period ago (consumers need tiles stored almost a layer earlier)
+					if (pending >= 0) {
+						asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+						publish(pending);
+					}
+					pending = l * n_waves + (tile - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x);
+				}
+				// with too few waves the next layer's first wave depends on this layer's last one
+				if (n_waves < wave_reach + 2 && pending >= 0) {
+					asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+					publish(pending);
+					pending = -1;
+				}
+			}
+			asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+			if (pending >= 0) publish(pending);
+			__threadfence();
+			// the last CTA to finish advances the epoch for the next launch
+			const unsigned int old = atomicAdd(p.sync_counter, 1u);
+			if (old == gridDim.x - 1u) {
+				atomicExch(p.sync_counter, 0u);
+				atomicAdd(p.sync_counter + 1, 1u);
+			}
+		}
 	} else if (warp == 1) {
 		// ===================== MMA issuer =====================
 		const uint32_t idesc = make_idesc(64);
@@ -272,27 +326,14 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 		const int coff = half * 4;
 		if (p.pdl) grid_dependency_wait();
 		int it = 0, rcount = 0;
-		int pending = -1;  // counter index of a stored tile that is not yet published (store thread only)
-		auto publish = [&](int idx) {
-			// the bulk store has completed: make it visible GPU-wide, then count the tile
-			asm volatile("fence.proxy.async;" ::: "memory");
-			__threadfence();
-			asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.flags + idx) : "memory");
-		};
 		for (int l = 0; l < p.n_layers; ++l) {
 			float bias_reg[32];
 #pragma unroll
 			for (int c = 0; c < 32; ++c) bias_reg[c] = __ldg(p.bias + l * 64 + half * 32 + c);
 			const bool has_res = (l & 1) != 0;
-			const CUtensorMap *mout = &maps.tile[layer_out(l)];
 			for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-				int b, y0, x0;
-				decode(tile, b, y0, x0);
 				const int as = it & 1;
 				const uint32_t aph = (it >> 1) & 1;
-				if (etid == 0 && it >= 2) {
-					asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-				}
 				mbar_wait(tfull_bar(as), aph, p.error_flag, 5);
 				tcgen05_fence_after();
 				uint32_t acc[32];
@@ -316,7 +357,7 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 					if (lane == 0) mbar_arrive(rempty_bar(rb));
 					++rcount;
 				}
-				epilogue_barrier<256>();  // staging[as] free (wait_group.read above)
+				mbar_wait(sfree_bar(as), aph ^ 1u, p.error_flag, 11);  // staging[as] consumed by the store of tile it-2
 				float v[32];
 #pragma unroll
 				for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(acc[c]) + bias_reg[c];
@@ -351,36 +392,10 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 					    *reinterpret_cast<uint32_t *>(&h1), *reinterpret_cast<uint32_t *>(&h2),
 					    *reinterpret_cast<uint32_t *>(&h3));
 				}
+				// generic-proxy smem writes -> visible to the TMA (async proxy), then hand the tile over
 				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-				epilogue_barrier<256>();
-				if (etid == 0) {
-					tma_store_4d(mout, epi_out_base + as * kEpiTile, 0, x0, y0, b);
-					// flags lag one tile behind the stores, so this thread never waits on a store it
-					// has just issued (consumers need tiles that were stored a whole layer earlier)
-					if (pending >= 0) {
-						asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
-						publish(pending);
-					}
-					pending = l * n_waves + (tile - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x);
-				}
-			}
-			// with too few waves the next layer's first wave depends on this layer's last one:
-			// publish it now instead of lazily (costs one store-completion wait per layer)
-			if (etid == 0 && n_waves < wave_reach + 2 && pending >= 0) {
-				asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-				publish(pending);
-				pending = -1;
-			}
-		}
-		if (etid == 0) {
-			asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-			if (pending >= 0) publish(pending);
-			__threadfence();
-			// the last CTA to finish advances the epoch for the next launch
-			const unsigned int old = atomicAdd(p.sync_counter, 1u);
-			if (old == gridDim.x - 1u) {
-				atomicExch(p.sync_counter, 0u);
-				atomicAdd(p.sync_counter + 1, 1u);
+				__syncwarp();
+				if (lane == 0) mbar_arrive(sready_bar(as));
 			}
 		}
 	}
@@ -412,7 +427,7 @@ EncodeTiledFn encodeTiledDF() {
 	return fn;
 }
 
-constexpr uint32_t kFixed = 1024u + 768u + kBBytes + 4u * kEpiTile;
+constexpr uint32_t kFixed = 1024u + 768u + kBBytes + 4u * kEpiTile;  // alignment slack, barriers, weights, staging
 
 }  // namespace
 
