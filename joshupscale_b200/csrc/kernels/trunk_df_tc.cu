@@ -231,9 +231,9 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 			int it = 0;
 			int pending = -1;  // counter index of a stored tile that is not yet published
 			auto publish = [&](int idx) {
-				// the bulk store has completed: make it visible GPU-wide, then count the tile
+				// the bulk store has completed (async proxy): order it before the generic-proxy
+				// release below, which makes it visible to every acquiring producer warp
 				asm volatile("fence.proxy.async;" ::: "memory");
-				__threadfence();
 				asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.flags + idx) : "memory");
 			};
 			for (int l = 0; l < p.n_layers; ++l) {
