@@ -2,15 +2,15 @@
 // layers of the generator's residual stack - scripts/training/models.py:193-254,
 // 544-550 - in one launch), but without any grid-wide barrier.
 //
-// A tile of layer l only needs the 3x3 tile neighbourhood of layer l-1, so every
-// stored tile publishes a generation number in its own flag word (st.release.gpu
-// once the TMA store has completed) and the TMA producer warp polls the <= 9
-// neighbour flags in parallel (one lane each, ld.acquire.gpu) before it requests
-// a halo.  With the static tile->CTA striding all CTAs advance in waves; the
-// neighbours of a wave-k tile belong to waves k-1..k+1 of the previous layer,
-// stored several tile periods earlier, so CTAs are only gated by their true
-// neighbours (never by the slowest CTA of the grid) and the producer prefetches
-// halos of layer l+1 while the MMAs of layer l still run.
+// A tile of layer l only needs the 3x3 tile neighbourhood of layer l-1.  With the
+// static tile->CTA striding (tile = cta + k*grid) all CTAs advance in waves k, and
+// the neighbours of a wave-k tile lie in waves k-1..k+1, so the dependency is kept
+// per (layer, wave): every completed TMA store bumps a counter (release), and the
+// TMA producer needs counter[l-1][k+1] to be full (acquire) before it requests a
+// halo of layer l, wave k - one cached poll per wave instead of a grid barrier.
+// Wave 0 of layer l+1 only needs waves 0..1 of layer l, which were stored almost a
+// whole layer earlier: in steady state no CTA waits at a layer boundary and the
+// producer prefetches halos of layer l+1 while the MMAs of layer l still run.
 //
 // The resident weights are swapped tap by tap: on a CTA's last tile of layer l the
 // MMA warp commits one barrier per tap, a dedicated loader warp refills that tap's
@@ -21,9 +21,9 @@
 // layers after it was read, and the read-after-write chain of the writer
 // (neighbours of neighbours) covers every reader of the old contents.
 //
-// Flags are never reset: generations are epoch * n_layers + layer + 1 with a
-// per-launch epoch kept in global memory (advanced by the last CTA to finish) and
-// compared wrap-safe, so the captured CUDA graph replays without any memset node.
+// Counters are never reset: launch number `epoch` (kept in global memory, advanced
+// by the last CTA to finish) expects (epoch+1) * tiles_in_wave, compared wrap-safe,
+// so the captured CUDA graph replays without any memset node.
 #include <cstring>
 
 #include "kernels.h"
@@ -55,7 +55,7 @@ struct TrunkParams {
 	int pdl;
 	const float *bias;            // [n_layers][64]
 	unsigned int *sync_counter;   // [0] finished-CTA counter, [1] launch epoch
-	unsigned int *flags;          // [total_tiles] generation of the last completed store per tile
+	unsigned int *flags;          // [n_layers][n_waves] stored-tile counters, never reset
 	int *error_flag;
 };
 
@@ -143,7 +143,6 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 
 	// launch epoch: identical for every CTA of this launch (advanced by the last CTA to finish)
 	const unsigned int epoch = *reinterpret_cast<volatile unsigned int *>(p.sync_counter + 1);
-	const unsigned int gen_base = epoch * static_cast<unsigned int>(p.n_layers);
 	const int n_waves = (p.total_tiles + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
 	// the 3x3 tile neighbourhood spans tile indices t +- (tiles_x + 1): that many waves ahead must be complete
 	const int wave_reach = (p.tiles_x + 1 + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
@@ -151,11 +150,8 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 	if (warp == 0) {
 		// ===================== TMA producer (warp converged; lanes 0..8 poll neighbour flags) =====
 		if (p.pdl) grid_dependency_wait();
-		const int dy = lane / 3 - 1, dx = lane % 3 - 1;  // neighbour polled by this lane (lanes 0..8)
 		int it = 0, tcount = 0;
 		for (int l = 0; l < p.n_layers; ++l) {
-			// generation a neighbour tile must have reached: layer l-1 of this launch
-			const unsigned int need = gen_base + static_cast<unsigned int>(l);
 			const CUtensorMap *min = &maps.in[layer_in(l)];
 			const int r = layer_res(l);
 			auto load_residual = [&](int tc, int tile) {
@@ -171,6 +167,7 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 				__syncwarp();
 			};
 			int prev_tile = -1;
+			int known = -1;  // highest wave of layer l-1 known to be completely stored
 			for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
 				int b, y0, x0;
 				decode(tile, b, y0, x0);
@@ -179,22 +176,26 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 				mbar_wait(empty_bar(s), ph ^ 1u, p.error_flag, 1);
 				bool polled = false;
 				if (l > 0) {
-					// the 3x3 tile neighbourhood of layer l-1 must be stored: lanes 0..8 poll one flag each
-					const int tx = x0 / kTileW + dx, ty = y0 / kTileH + dy;
-					const bool check = lane < 9 && tx >= 0 && tx < p.tiles_x && ty >= 0 && ty < p.tiles_y;
-					const unsigned int *flag =
-					    p.flags + (static_cast<size_t>(b) * p.tiles_y + (check ? ty : 0)) * p.tiles_x + (check ? tx : 0);
-					unsigned int spins = 0;
-					while (true) {
-						const bool ok = !check || static_cast<int>(ld_acquire_gpu(flag) - need) >= 0;
-						if (__all_sync(0xffffffffu, ok)) break;
-						__nanosleep(32);
-						if (++spins > (1u << 24)) {
-							if (p.error_flag) atomicExch(p.error_flag, 8);
-							__trap();
+					// waves <= k+1 of layer l-1 must be completely stored (covers the 3x3 neighbourhood)
+					const int k = (tile - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x);
+					const int needw = k + wave_reach < n_waves ? k + wave_reach : n_waves - 1;
+					while (known < needw) {
+						const int wv = known + 1;
+						const int cnt = wv + 1 < n_waves ? static_cast<int>(gridDim.x)
+						                                 : p.total_tiles - wv * static_cast<int>(gridDim.x);
+						const unsigned int target = (epoch + 1u) * static_cast<unsigned int>(cnt);
+						const unsigned int *ctr = p.flags + (l - 1) * n_waves + wv;
+						unsigned int spins = 0;
+						while (static_cast<int>(ld_acquire_gpu(ctr) - target) < 0) {
+							__nanosleep(32);
+							if (++spins > (1u << 24)) {
+								if (p.error_flag) atomicExch(p.error_flag, 8);
+								__trap();
+							}
 						}
+						known = wv;
+						polled = true;
 					}
-					polled = true;
 				}
 				if (lane == 0) {
 					if (polled) {
@@ -228,13 +229,12 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 		if (lane == 0) {
 			if (p.pdl) grid_dependency_wait();
 			int it = 0;
-			int pending = -1;  // tile whose store is in flight and whose flag is not yet raised
-			unsigned int pending_gen = 0;
+			int pending = -1;  // counter index of a stored tile that is not yet published
 			auto publish = [&](int idx) {
 				// the bulk store has completed (async proxy): order it before the generic-proxy
 				// release below, which makes it visible to every acquiring producer warp
 				asm volatile("fence.proxy.async;" ::: "memory");
-				asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.flags + idx), "r"(pending_gen) : "memory");
+				asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.flags + idx) : "memory");
 			};
 			for (int l = 0; l < p.n_layers; ++l) {
 				const CUtensorMap *mout = &maps.tile[layer_out(l)];
@@ -253,8 +253,7 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 						asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
 						publish(pending);
 					}
-					pending = tile;
-					pending_gen = gen_base + static_cast<unsigned int>(l) + 1u;
+					pending = l * n_waves + (tile - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x);
 				}
 				// with too few waves the next layer's first wave depends on this layer's last one
 				if (n_waves < wave_reach + 2 && pending >= 0) {
