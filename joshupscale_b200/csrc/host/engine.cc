@@ -36,6 +36,7 @@ Engine::Engine(const ModelFile &model, int device, int batch)
 		JU_LOG_WARN << "device " << device << " is sm_" << prop.major << prop.minor
 		            << "; kernels are built for sm_100a only";
 	}
+	m_SmCount = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 1;
 	m_ConvImpl = envInt("JU_CONV_IMPL", 1);  // 1 = tcgen05 (default), 0 = SIMT reference kernels
 	if (const char *v = std::getenv("JU_TC_VARIANT")) conv_tc_set_variant(std::atoi(v));
 	if (const char *v = std::getenv("JU_TC_TMA_EPILOGUE")) conv_tc_set_flags(std::atoi(v), -1);
@@ -464,8 +465,12 @@ void Engine::buildPlan(int parity) {
 		ta.act = first->act;
 		ta.slope = first->slope;
 		TrunkTcLaunch launch;
-		// JU_TRUNK_SYNC: 1 = per-tile dataflow flags (trunk_df_tc.cu), 0 = grid barrier per layer (trunk_tc.cu)
-		const bool dataflow = envInt("JU_TRUNK_SYNC", 0) != 0;
+		// JU_TRUNK_SYNC: 1 = per-wave dataflow counters (trunk_df_tc.cu), 0 = grid barrier per layer
+		// (trunk_tc.cu), -1 (default) = dataflow for short layers (few tile waves per CTA, where the
+		// barrier bubble matters) and the barrier for large batches, which it keeps L2-coherent
+		const int syncMode = envInt("JU_TRUNK_SYNC", -1);
+		const int tileWaves = (B * ((H + 15) / 16) * ((W + 7) / 8) + m_SmCount - 1) / m_SmCount;
+		const bool dataflow = syncMode < 0 ? tileWaves <= envInt("JU_TRUNK_DF_MAX_WAVES", 8) : syncMode != 0;
 		checkCuda(dataflow ? trunk_df_tc_prepare(ta, &launch) : trunk_tc_prepare(ta, &launch), "trunk_tc_prepare");
 		Op op;
 		op.name = "generator/block_*(persistent)";

@@ -91,6 +91,7 @@ private:
 	ModelSpec m_Spec;
 	int m_Device = 0;
 	int m_Batch = 1;
+	int m_SmCount = 1;
 	int m_ConvImpl = 0;
 	bool m_UseGraph = true;
 	bool m_Conv2Cta = false;
