@@ -44,6 +44,7 @@ constexpr uint32_t kARegion = (kABox + 1023u) & ~1023u;
 constexpr uint32_t kBSlice = 64u * 128u;
 constexpr uint32_t kBBytes = 9u * kBSlice;  // one layer's weights
 constexpr uint32_t kEpiTile = 128u * 128u;
+constexpr int kAccStages = 4;  // TMEM accumulator stages of 64 columns
 
 struct TrunkParams {
 	int batch, h, w;
@@ -57,13 +58,23 @@ struct TrunkParams {
 	unsigned int *sync_counter;   // [0] finished-CTA counter, [1] launch epoch
 	unsigned int *flags;          // [n_layers][n_waves] stored-tile counters, never reset
 	int *error_flag;
+	const __half *buffers[3];     // T0, T1, T2 (residual rows are read straight from global memory)
+	int cstride;
 };
 
 struct TrunkMaps {
 	CUtensorMap in[3];    // halo boxes (64 ch, 10, 18, 1) over T0, T1, T2
-	CUtensorMap tile[3];  // pixel tiles (64 ch, 8, 16, 1) over T0, T1, T2: residual loads and output stores
+	CUtensorMap tile[3];  // pixel tiles (64 ch, 8, 16, 1) over T0, T1, T2: output stores
 	CUtensorMap w;        // weights of all layers: rows [layer][tap][cout], 64 ch each
 };
+
+// 32 bytes (16 channels) from L2, bypassing L1
+__device__ __forceinline__ void ld_global_256(const __half *p, uint4 &a, uint4 &b) {
+	asm volatile("ld.global.cg.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+	             : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+	             : "l"(p)
+	             : "memory");
+}
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p) {
 	unsigned int v;
@@ -78,15 +89,12 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 	uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 	const uint32_t resb_base = smem_base + static_cast<uint32_t>(p.stages) * kARegion;
 	const uint32_t epi_out_base = resb_base + kBBytes;
-	const uint32_t epi_res_base = epi_out_base + 2u * kEpiTile;
-	const uint32_t bar_base = epi_res_base + 2u * kEpiTile;
+	const uint32_t bar_base = epi_out_base + 2u * kEpiTile;
 	auto full_bar = [&](int s) { return bar_base + 8u * s; };
 	auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
 	auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
-	auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 2 + s); };
-	const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 5);
-	auto rfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 6 + s); };
-	auto rempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 8 + s); };
+	auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + kAccStages + s); };
+	const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 8);
 	auto wfull_tap = [&](int t) { return bar_base + 8u * (2 * kMaxStages + 10 + t); };
 	auto wempty_tap = [&](int t) { return bar_base + 8u * (2 * kMaxStages + 19 + t); };
 	auto sready_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 28 + s); };  // staging tile written
@@ -94,18 +102,18 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 
 	const int warp = threadIdx.x >> 5;
 	const int lane = threadIdx.x & 31;
-	constexpr uint32_t kTmemCols = 128;
+	constexpr uint32_t kTmemCols = 64u * kAccStages;
 
 	if (warp == 0 && lane == 0) {
 		for (int s = 0; s < p.stages; ++s) {
 			mbar_init(full_bar(s), 1);
 			mbar_init(empty_bar(s), 1);
 		}
-		for (int s = 0; s < 2; ++s) {
+		for (int s = 0; s < kAccStages; ++s) {
 			mbar_init(tfull_bar(s), 1);
 			mbar_init(tempty_bar(s), 8);
-			mbar_init(rfull_bar(s), 1);
-			mbar_init(rempty_bar(s), 8);
+		}
+		for (int s = 0; s < 2; ++s) {
 			mbar_init(sready_bar(s), 8);
 			mbar_init(sfree_bar(s), 1);
 		}
@@ -150,23 +158,9 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 	if (warp == 0) {
 		// ===================== TMA producer (warp converged; lanes 0..8 poll neighbour flags) =====
 		if (p.pdl) grid_dependency_wait();
-		int it = 0, tcount = 0;
+		int it = 0;
 		for (int l = 0; l < p.n_layers; ++l) {
 			const CUtensorMap *min = &maps.in[layer_in(l)];
-			const int r = layer_res(l);
-			auto load_residual = [&](int tc, int tile) {
-				int b, y0, x0;
-				decode(tile, b, y0, x0);
-				const int rb = tc & 1;
-				const uint32_t rph = (tc >> 1) & 1;
-				mbar_wait(rempty_bar(rb), rph ^ 1u, p.error_flag, 6);
-				if (lane == 0) {
-					mbar_arrive_expect_tx(rfull_bar(rb), kEpiTile);
-					tma_load_4d(epi_res_base + rb * kEpiTile, &maps.tile[r], rfull_bar(rb), 0, x0, y0, b);
-				}
-				__syncwarp();
-			};
-			int prev_tile = -1;
 			int known = -1;  // highest wave of layer l-1 known to be completely stored
 			for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
 				int b, y0, x0;
@@ -206,10 +200,7 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 					tma_load_4d(smem_base + s * kARegion, min, full_bar(s), 0, x0 - 1, y0 - 1, b);
 				}
 				__syncwarp();
-				if (r >= 0 && prev_tile >= 0) load_residual(tcount++, prev_tile);
-				prev_tile = tile;
 			}
-			if (r >= 0 && prev_tile >= 0) load_residual(tcount++, prev_tile);
 		}
 	} else if (warp == 10) {
 		// ===================== weight loader: tap slices follow the MMA warp layer by layer ======
@@ -282,8 +273,8 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 		for (int l = 0; l < p.n_layers; ++l) {
 			bool first = true;
 			for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-				const int as = it & 1;
-				const uint32_t aph = (it >> 1) & 1;
+				const int as = it % kAccStages;
+				const uint32_t aph = (it / kAccStages) & 1;
 				mbar_wait(tempty_bar(as), aph ^ 1u, p.error_flag, 3);
 				const int s = it % p.stages;
 				const uint32_t ph = (it / p.stages) & 1;
@@ -325,15 +316,36 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 		const uint32_t sw = static_cast<uint32_t>(row & 7);
 		const int coff = half * 4;
 		if (p.pdl) grid_dependency_wait();
-		int it = 0, rcount = 0;
+		int it = 0;
 		for (int l = 0; l < p.n_layers; ++l) {
 			float bias_reg[32];
 #pragma unroll
 			for (int c = 0; c < 32; ++c) bias_reg[c] = __ldg(p.bias + l * 64 + half * 32 + c);
 			const bool has_res = (l & 1) != 0;
+			const __half *res_buf = has_res ? p.buffers[layer_res(l)] : nullptr;
 			for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-				const int as = it & 1;
-				const uint32_t aph = (it >> 1) & 1;
+				const int as = it % kAccStages;
+				const uint32_t aph = (it / kAccStages) & 1;
+				const int ss = it & 1;  // staging tile
+				const uint32_t sph = (it >> 1) & 1;
+				// The shortcut row comes straight from global memory (L2) and never touches shared
+				// memory, whose port the MMA operand fetch saturates.  It was stored two layers ago
+				// by this CTA's own TMA stores; requested before the accumulator wait, so the
+				// latency hides behind the MMAs of this tile.
+				uint4 res[4];
+				if (has_res) {
+					int b, y0, x0;
+					decode(tile, b, y0, x0);
+					const int y = y0 + (row >> 3), x = x0 + (row & 7);
+					if (y < p.h && x < p.w) {
+						const __half *src = res_buf +
+						    ((static_cast<size_t>(b) * p.h + y) * p.w + x) * static_cast<size_t>(p.cstride) + half * 32;
+						ld_global_256(src, res[0], res[1]);
+						ld_global_256(src + 16, res[2], res[3]);
+					} else {
+						res[0] = res[1] = res[2] = res[3] = make_uint4(0u, 0u, 0u, 0u);
+					}
+				}
 				mbar_wait(tfull_bar(as), aph, p.error_flag, 5);
 				tcgen05_fence_after();
 				uint32_t acc[32];
@@ -345,19 +357,7 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 				tcgen05_fence_before();
 				__syncwarp();
 				if (lane == 0) mbar_arrive(tempty_bar(as));
-				uint4 res[4];
-				if (has_res) {
-					const int rb = rcount & 1;
-					mbar_wait(rfull_bar(rb), static_cast<uint32_t>((rcount >> 1) & 1), p.error_flag, 7);
-					const uint4 *res_row = reinterpret_cast<const uint4 *>(
-					    smem_gen + (epi_res_base - smem_base) + rb * kEpiTile + row * 128u);
-#pragma unroll
-					for (int c = 0; c < 4; ++c) res[c] = res_row[(coff + c) ^ sw];
-					__syncwarp();
-					if (lane == 0) mbar_arrive(rempty_bar(rb));
-					++rcount;
-				}
-				mbar_wait(sfree_bar(as), aph ^ 1u, p.error_flag, 11);  // staging[as] consumed by the store of tile it-2
+				mbar_wait(sfree_bar(ss), sph ^ 1u, p.error_flag, 11);  // staging[ss] consumed by the store of tile it-2
 				float v[32];
 #pragma unroll
 				for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(acc[c]) + bias_reg[c];
@@ -381,7 +381,7 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 					for (int c = 0; c < 32; ++c) v[c] = v[c] >= 0.f ? v[c] : v[c] * p.slope;
 				}
 				uint4 *out_row = reinterpret_cast<uint4 *>(
-				    smem_gen + (epi_out_base - smem_base) + as * kEpiTile + row * 128u);
+				    smem_gen + (epi_out_base - smem_base) + ss * kEpiTile + row * 128u);
 #pragma unroll
 				for (int c = 0; c < 4; ++c) {
 					__half2 h0 = __floats2half2_rn(v[c * 8 + 0], v[c * 8 + 1]);
@@ -395,7 +395,7 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 				// generic-proxy smem writes -> visible to the TMA (async proxy), then hand the tile over
 				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 				__syncwarp();
-				if (lane == 0) mbar_arrive(sready_bar(as));
+				if (lane == 0) mbar_arrive(sready_bar(ss));
 			}
 		}
 	}
@@ -427,7 +427,7 @@ EncodeTiledFn encodeTiledDF() {
 	return fn;
 }
 
-constexpr uint32_t kFixed = 1024u + 768u + kBBytes + 4u * kEpiTile;  // alignment slack, barriers, weights, staging
+constexpr uint32_t kFixed = 1024u + 768u + kBBytes + 2u * kEpiTile;  // alignment slack, barriers, weights, staging
 
 }  // namespace
 
@@ -452,6 +452,8 @@ cudaError_t trunk_df_tc_prepare(const TrunkArgs &a, TrunkTcLaunch *out) {
 	p.sync_counter = a.sync_counter;
 	p.flags = a.flags;
 	if (!a.flags) return cudaErrorInvalidValue;
+	for (int i = 0; i < 3; ++i) p.buffers[i] = static_cast<const __half *>(a.buffers[i]);
+	p.cstride = a.cstride;
 	int stages = static_cast<int>((kSmemLimit - kFixed) / kARegion);
 	if (stages > kMaxStages) stages = kMaxStages;
 	if (stages < 2) return cudaErrorInvalidValue;
