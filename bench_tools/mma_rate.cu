@@ -12,10 +12,11 @@ using namespace ju::tc;
 // mode 0: conv-like (A = shifted views of one 18x10 halo, SBO 1280; B = 9 resident tap slices)
 // mode 1: plain GEMM-like (A tile 128 rows x 128 B, SBO 1024, same tile every time)
 template <int N>
-__global__ void __launch_bounds__(64, 1) mma_rate_kernel(int iters, int mode, int lsu_noise, long long *cycles) {
+__global__ void __launch_bounds__(384, 1) mma_rate_kernel(int iters, int mode, int lsu_noise, int fill, long long *cycles) {
 	extern __shared__ __align__(1024) unsigned char smem_raw[];
 	__shared__ uint32_t tmem_slot;
 	__shared__ __align__(8) unsigned long long bar;
+	__shared__ __align__(8) unsigned long long dummy_bar[2];
 	const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
 	const uint32_t a_base = base;                 // 18*10*128 = 23040 B -> 24 KB
 	const uint32_t w_base = base + 24 * 1024;     // 9 * N * 128 B
@@ -26,22 +27,37 @@ __global__ void __launch_bounds__(64, 1) mma_rate_kernel(int iters, int mode, in
 	}
 	if (threadIdx.x == 0) {
 		mbar_init(smem_u32(&bar), 1);
+		mbar_init(smem_u32(&dummy_bar[0]), 1);
+		mbar_init(smem_u32(&dummy_bar[1]), 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	tcgen05_fence_before();
 	__syncthreads();
 	tcgen05_fence_after();
+	if (fill) {
+		// pseudo-random fp16 data in [-1, 1): data-dependent power / throttling shows up as slower MMAs
+		uint32_t x = 0x9E3779B9u * (threadIdx.x + 1) + blockIdx.x;
+		uint32_t *w = reinterpret_cast<uint32_t *>(smem_raw);
+		const int words = (1024 + 24 * 1024 + 9 * N * 128) / 4;
+		for (int i = threadIdx.x; i < words; i += blockDim.x) {
+			x = x * 1664525u + 1013904223u;
+			const uint32_t lo = 0x3800u | ((x >> 3) & 0x83FFu), hi = 0x3800u | ((x >> 17) & 0x83FFu);
+			w[i] = lo | (hi << 16);
+		}
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+		__syncthreads();
+	}
 	const uint32_t tmem = tmem_slot;
 	const uint32_t idesc = make_idesc(N);
 	if (warp == 0) {
 		long long t0 = clock64();
 		for (int it = 0; it < iters; ++it) {
-			const uint32_t d = tmem + (it & 1) * N;
+			const uint32_t d = tmem + ((mode & 4) ? (it & 3) : (it & 1)) * N;
 #pragma unroll
 			for (int tap = 0; tap < 9; ++tap) {
 				const int dy = tap / 3, dx = tap % 3;
-				const uint32_t a0 = mode == 0 ? a_base + (dy * 10 + dx) * 128 : a_base;
-				const uint32_t sbo = mode == 0 ? 1280u : 1024u;
+				const uint32_t a0 = !(mode & 1) ? a_base + (dy * 10 + dx) * 128 : a_base;
+				const uint32_t sbo = !(mode & 1) ? 1280u : 1024u;
 				const uint32_t b0 = w_base + tap * N * 128;
 #pragma unroll
 				for (int ks = 0; ks < 4; ++ks) {
@@ -52,12 +68,40 @@ __global__ void __launch_bounds__(64, 1) mma_rate_kernel(int iters, int mode, in
 					__syncwarp();
 				}
 			}
+			if (mode & 2) {
+				if (elect_one_sync()) {
+					umma_commit(smem_u32(&dummy_bar[0]));
+					umma_commit(smem_u32(&dummy_bar[1]));
+				}
+				__syncwarp();
+			}
 		}
 		if (elect_one_sync()) umma_commit(smem_u32(&bar));
 		__syncwarp();
 		mbar_wait(smem_u32(&bar), 0, nullptr, 0);
 		long long t1 = clock64();
 		if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+	} else if (lsu_noise == -2 || lsu_noise == -3) {
+		// polling warps: spin on an mbarrier phase that never completes, like idle pipeline stages do
+		long long t0 = clock64();
+		uint32_t fails = 0;
+		const int n = iters * 36;
+		for (int i = 0; i < n; ++i) {
+			if (!mbar_try_wait(smem_u32(&dummy_bar[1]), 0)) ++fails;
+			if (lsu_noise == -3) __nanosleep(64);
+		}
+		long long t1 = clock64();
+		if (threadIdx.x == 32 && blockIdx.x == 0) cycles[148] = (t1 - t0) / n;
+		if (fails == 0x12345678) cycles[0] = 0;
+	} else if (lsu_noise < 0) {
+		uint32_t r[32];
+		uint32_t acc = 0;
+		for (int i = 0; i < iters * 8; ++i) {
+			tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (i & 3) * 64, r);
+			tmem_ld_wait();
+			acc += r[0] + r[31];
+		}
+		if (acc == 0x12345678) cycles[0] = 0;
 	} else if (lsu_noise) {
 		// a second warp hammering shared memory with conflict-free 128-bit loads/stores
 		uint32_t addr = base + 24 * 1024 + 9 * N * 128 + (threadIdx.x & 31) * 16;
@@ -77,32 +121,43 @@ __global__ void __launch_bounds__(64, 1) mma_rate_kernel(int iters, int mode, in
 	}
 }
 
+#define N_TMEM_NOISE 1
 template <int N>
-void run(int mode, int noise) {
-	const int iters = 200;
+void run(int mode, int noise, int fill = 0) {
+	const int iters = 2000;
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0);
+	cudaEventCreate(&e1);
 	long long *d;
-	cudaMalloc(&d, 148 * sizeof(long long));
+	cudaMalloc(&d, 149 * sizeof(long long));
+	cudaMemset(d, 0, 149 * sizeof(long long));
 	const int smem = 1024 + 24 * 1024 + 9 * N * 128 + 16 * 1024;
 	cudaFuncSetAttribute(mma_rate_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-	for (int rep = 0; rep < 2; ++rep) mma_rate_kernel<N><<<148, 64, smem>>>(iters, mode, noise, d);
+	mma_rate_kernel<N><<<148, 384, smem>>>(iters, mode, noise, fill, d);
+	cudaEventRecord(e0);
+	for (int rep = 0; rep < 1; ++rep) mma_rate_kernel<N><<<148, 384, smem>>>(iters, mode, noise, fill, d);
+	cudaEventRecord(e1);
 	cudaError_t e = cudaDeviceSynchronize();
-	long long h[148];
+	float ms = 0;
+	cudaEventElapsedTime(&ms, e0, e1);
+	long long h[149];
 	cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
 	double s = 0;
 	for (int i = 0; i < 148; ++i) s += h[i];
 	const double per = s / 148 / (iters * 36.0);
-	printf("N=%3d mode=%d noise=%d: %.1f cycles/MMA  (%.0f cycles per 36-MMA tile, %.0f MAC/clk/SM) %s\n", N, mode, noise, per,
-	    per * 36, 128.0 * N * 16 / per, e == cudaSuccess ? "" : cudaGetErrorString(e));
+	printf("N=%3d mode=%d noise=%d fill=%d: %.1f cycles/MMA  (%.0f cycles per 36-MMA tile, %.0f MAC/clk/SM), %.1f ns/MMA => %.2f GHz, %.0f TFLOP/s %s\n",
+	    N, mode, noise, fill, per, per * 36, 128.0 * N * 16 / per, ms * 1e6 / (iters * 36.0), per / (ms * 1e6 / (iters * 36.0)),
+	    148.0 * 2 * 128 * N * 16 * iters * 36 / (ms * 1e-3) / 1e12, e == cudaSuccess ? "" : cudaGetErrorString(e));
+	if (noise <= -2) printf("   (failed try_wait: %lld cycles per poll, %d polling warps)\n", h[148], 384 / 32 - 1);
 	cudaFree(d);
 }
 
 int main() {
-	for (int mode = 0; mode < 2; ++mode) {
-		run<32>(mode, 0);
-		run<64>(mode, 0);
-		run<128>(mode, 0);
-		run<256>(mode, 0);
-	}
-	run<64>(0, 100000);
+	run<64>(0, 0, 1);
+	run<64>(2, 0, 1);
+	run<64>(4, 0, 1);
+	run<64>(6, 0, 1);
+	run<64>(4, -2, 1);
+	run<64>(4, -3, 1);
 	return 0;
 }

@@ -40,6 +40,19 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
 	return ok;
 }
 
+// non-blocking phase test
+__device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity) {
+	uint32_t ok;
+	asm volatile(
+	    "{\n\t.reg .pred p;\n\t"
+	    "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+	    "selp.u32 %0, 1, 0, p;\n\t}"
+	    : "=r"(ok)
+	    : "r"(bar), "r"(parity)
+	    : "memory");
+	return ok;
+}
+
 // Bounded wait: a protocol bug must surface as an error, never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int *error_flag, int code) {
 	for (uint32_t i = 0; i < (1u << 22); ++i) {

@@ -24,6 +24,8 @@
 // Counters are never reset: launch number `epoch` (kept in global memory, advanced
 // by the last CTA to finish) expects (epoch+1) * tiles_in_wave, compared wrap-safe,
 // so the captured CUDA graph replays without any memset node.
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "kernels.h"
@@ -36,7 +38,10 @@ namespace {
 using namespace tc;
 
 constexpr int kTileH = 16, kTileW = 8;
-constexpr int kThreadsT = 384;  // producer, MMA, 8 epilogue warps, weight-loader warp, store/publish warp
+constexpr int kStoreWarps = 3;  // one staging tile each
+constexpr int kSecondMmaWarp = 11 + kStoreWarps;
+constexpr int kSecondProducerWarp = kSecondMmaWarp + 1;
+constexpr int kThreadsT = 32 * (kSecondProducerWarp + 1);  // producer, MMA, 8 epilogue warps, weight loader, store/publish warps, 2nd MMA warp
 constexpr int kMaxStages = 8;
 constexpr uint32_t kSmemLimit = 227 * 1024;
 constexpr uint32_t kABox = 18u * 10u * 128u;
@@ -60,6 +65,7 @@ struct TrunkParams {
 	int *error_flag;
 	const __half *buffers[3];     // T0, T1, T2 (residual rows are read straight from global memory)
 	int cstride;
+	int ablate;  // timing experiments only (JU_TRUNK_ABLATE bit mask); results are wrong when non-zero
 };
 
 struct TrunkMaps {
@@ -76,6 +82,18 @@ __device__ __forceinline__ void ld_global_256(const __half *p, uint4 &a, uint4 &
 	             : "memory");
 }
 
+__device__ __forceinline__ long long gtime() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return static_cast<long long>(t);
+}
+
+__device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int *p) {
+	unsigned int v;
+	asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p) {
 	unsigned int v;
 	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -89,7 +107,7 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 	uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 	const uint32_t resb_base = smem_base + static_cast<uint32_t>(p.stages) * kARegion;
 	const uint32_t epi_out_base = resb_base + kBBytes;
-	const uint32_t bar_base = epi_out_base + 2u * kEpiTile;
+	const uint32_t bar_base = epi_out_base + kStoreWarps * kEpiTile;
 	auto full_bar = [&](int s) { return bar_base + 8u * s; };
 	auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
 	auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
@@ -97,8 +115,8 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 	const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 8);
 	auto wfull_tap = [&](int t) { return bar_base + 8u * (2 * kMaxStages + 10 + t); };
 	auto wempty_tap = [&](int t) { return bar_base + 8u * (2 * kMaxStages + 19 + t); };
-	auto sready_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 28 + s); };  // staging tile written
-	auto sfree_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 30 + s); };   // staging tile read by the TMA store
+	auto sready_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 28 + s); };  // staging tile written (s < 4)
+	auto sfree_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 32 + s); };   // staging tile read by the TMA store
 
 	const int warp = threadIdx.x >> 5;
 	const int lane = threadIdx.x & 31;
@@ -113,13 +131,13 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 			mbar_init(tfull_bar(s), 1);
 			mbar_init(tempty_bar(s), 8);
 		}
-		for (int s = 0; s < 2; ++s) {
+		for (int s = 0; s < kStoreWarps; ++s) {
 			mbar_init(sready_bar(s), 8);
 			mbar_init(sfree_bar(s), 1);
 		}
 		for (int t = 0; t < 9; ++t) {
 			mbar_init(wfull_tap(t), 1);
-			mbar_init(wempty_tap(t), 1);
+			mbar_init(wempty_tap(t), 2);
 		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
@@ -129,6 +147,8 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 		             : "memory");
 		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 	}
+	long long &t_base = *reinterpret_cast<long long *>(smem_gen + (bar_base - smem_base) + 8u * (2 * kMaxStages + 9));
+	if (threadIdx.x == 0) t_base = gtime();
 	tcgen05_fence_before();
 	__syncthreads();
 	tcgen05_fence_after();
@@ -155,19 +175,26 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 	// the 3x3 tile neighbourhood spans tile indices t +- (tiles_x + 1): that many waves ahead must be complete
 	const int wave_reach = (p.tiles_x + 1 + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
 
-	if (warp == 0) {
+	if (warp == 0 || warp == kSecondProducerWarp) {
+		const int pme = warp == 0 ? 0 : 1;  // two producers, alternating tiles
 		// ===================== TMA producer (warp converged; lanes 0..8 poll neighbour flags) =====
 		if (p.pdl) grid_dependency_wait();
 		int it = 0;
+		constexpr int kTraceP = 64;
+		long long tp0[kTraceP], tp1[kTraceP], tp2[kTraceP];
+		const bool trace = (p.ablate & 16) && (blockIdx.x == 5 || blockIdx.x == 70 || blockIdx.x == 131 || blockIdx.x == 140);
 		for (int l = 0; l < p.n_layers; ++l) {
 			const CUtensorMap *min = &maps.in[layer_in(l)];
 			int known = -1;  // highest wave of layer l-1 known to be completely stored
 			for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
 				int b, y0, x0;
 				decode(tile, b, y0, x0);
+				if ((it & 1) != pme) continue;
 				const int s = it % p.stages;
 				const uint32_t ph = (it / p.stages) & 1;
+				if (trace && it < kTraceP) tp0[it] = gtime();
 				mbar_wait(empty_bar(s), ph ^ 1u, p.error_flag, 1);
+				if (trace && it < kTraceP) tp1[it] = gtime();
 				bool polled = false;
 				if (l > 0) {
 					// waves <= k+1 of layer l-1 must be completely stored (covers the 3x3 neighbourhood)
@@ -179,14 +206,16 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 						                                 : p.total_tiles - wv * static_cast<int>(gridDim.x);
 						const unsigned int target = (epoch + 1u) * static_cast<unsigned int>(cnt);
 						const unsigned int *ctr = p.flags + (l - 1) * n_waves + wv;
+						// spin on relaxed loads (no L1 invalidation per poll), then acquire once
 						unsigned int spins = 0;
-						while (static_cast<int>(ld_acquire_gpu(ctr) - target) < 0) {
+						while (static_cast<int>(ld_relaxed_gpu(ctr) - target) < 0) {
 							__nanosleep(32);
 							if (++spins > (1u << 24)) {
 								if (p.error_flag) atomicExch(p.error_flag, 8);
 								__trap();
 							}
 						}
+						(void)ld_acquire_gpu(ctr);
 						known = wv;
 						polled = true;
 					}
@@ -196,10 +225,21 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 						// order the async-proxy (TMA) reads below after the acquire loads above
 						asm volatile("fence.proxy.async;" ::: "memory");
 					}
-					mbar_arrive_expect_tx(full_bar(s), kABox);
-					tma_load_4d(smem_base + s * kARegion, min, full_bar(s), 0, x0 - 1, y0 - 1, b);
+					if (p.ablate & 4) {
+						mbar_arrive(full_bar(s));
+					} else {
+						mbar_arrive_expect_tx(full_bar(s), kABox);
+						tma_load_4d(smem_base + s * kARegion, min, full_bar(s), 0, x0 - 1, y0 - 1, b);
+					}
 				}
 				__syncwarp();
+				if (trace && it < kTraceP) tp2[it] = gtime();
+			}
+		}
+		if (trace && lane == 0) {
+			for (int i = 0; i < kTraceP && i < it; ++i) {
+				if ((i & 1) != pme) continue;
+				printf("C%d PRO %d t0 %lld empty %lld issued %lld\n", (int)blockIdx.x, i, tp0[i] % 100000000, tp1[i] % 100000000, tp2[i] % 100000000);
 			}
 		}
 	} else if (warp == 10) {
@@ -213,82 +253,98 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 				}
 			}
 		}
-	} else if (warp == 11) {
-		// ===================== store + publish warp =====================
-		// Issues the TMA store of every finished tile and publishes its completion, so no
-		// epilogue warp ever waits on a store or on a GPU-scope fence.
+	} else if (warp >= 11 && warp < 11 + kStoreWarps) {
+		// ===================== store + publish warps =====================
+		// kStoreWarps warps take the finished tiles round-robin: TMA store, wait for its completion,
+		// publish (GPU-scope release, ~1 us) - so no epilogue warp ever waits on a store or a fence,
+		// and the publish latency of one tile overlaps the stores of the next ones.
 		if (lane == 0) {
 			if (p.pdl) grid_dependency_wait();
+			const int me = warp - 11;
 			int it = 0;
-			int pending = -1;  // counter index of a stored tile that is not yet published
-			auto publish = [&](int idx) {
-				// the bulk store has completed (async proxy): order it before the generic-proxy
-				// release below, which makes it visible to every acquiring producer warp
-				asm volatile("fence.proxy.async;" ::: "memory");
-				asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.flags + idx) : "memory");
-			};
+			constexpr int kTraceS = 64;
+			long long ts0[kTraceS], ts1[kTraceS], ts2[kTraceS];
+			const bool trace = (p.ablate & 16) && (blockIdx.x == 5 || blockIdx.x == 70 || blockIdx.x == 131 || blockIdx.x == 140) && me == 0;
 			for (int l = 0; l < p.n_layers; ++l) {
 				const CUtensorMap *mout = &maps.tile[layer_out(l)];
 				for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+					if (it % kStoreWarps != me) continue;
 					int b, y0, x0;
 					decode(tile, b, y0, x0);
-					const int as = it & 1;
-					const uint32_t aph = (it >> 1) & 1;
+					const int as = me;  // this warp's staging tile
+					const uint32_t aph = (it / kStoreWarps) & 1;
 					mbar_wait(sready_bar(as), aph, p.error_flag, 10);
-					tma_store_4d(mout, epi_out_base + as * kEpiTile, 0, x0, y0, b);
+					if (trace && it < kTraceS) ts0[it] = gtime();
+					if (!(p.ablate & 2)) tma_store_4d(mout, epi_out_base + as * kEpiTile, 0, x0, y0, b);
 					asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem tile consumed
 					mbar_arrive(sfree_bar(as));
-					// counters lag one tile behind the stores: the store waited for here was issued a
-					// whole tile period ago (consumers need tiles stored almost a layer earlier)
-					if (pending >= 0) {
-						asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
-						publish(pending);
-					}
-					pending = l * n_waves + (tile - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x);
-				}
-				// with too few waves the next layer's first wave depends on this layer's last one
-				if (n_waves < wave_reach + 2 && pending >= 0) {
-					asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-					publish(pending);
-					pending = -1;
+					if (trace && it < kTraceS) ts1[it] = gtime();
+					asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // global writes complete
+					// the bulk store has completed (async proxy): order it before the generic-proxy
+					// release below, which makes it visible to every acquiring producer warp
+					asm volatile("fence.proxy.async;" ::: "memory");
+					asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(
+					                 p.flags + l * n_waves +
+					                 (tile - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x))
+					             : "memory");
+					if (trace && it < kTraceS) ts2[it] = gtime();
 				}
 			}
-			asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-			if (pending >= 0) publish(pending);
+			if (trace) {
+				for (int i = 0; i < kTraceS && i < it; i += kStoreWarps) {
+					printf("C%d STO %d sready %lld sfree %lld published %lld\n", (int)blockIdx.x, i, ts0[i] % 100000000, ts1[i] % 100000000, ts2[i] % 100000000);
+				}
+			}
 			__threadfence();
-			// the last CTA to finish advances the epoch for the next launch
+			// the last store warp of the last CTA to finish advances the epoch for the next launch
 			const unsigned int old = atomicAdd(p.sync_counter, 1u);
-			if (old == gridDim.x - 1u) {
+			if (old == gridDim.x * kStoreWarps - 1u) {
 				atomicExch(p.sync_counter, 0u);
 				atomicAdd(p.sync_counter + 1, 1u);
 			}
 		}
-	} else if (warp == 1) {
-		// ===================== MMA issuer =====================
+	} else if (warp == 1 || warp == kSecondMmaWarp) {
+		// ===================== MMA issuers (two warps, alternating tiles) =====================
+		// A barrier check has to get through the shared-memory pipe that the UMMA operand fetch
+		// saturates (~300 cycles each) and the tensor pipe only queues ~4 instructions, so a single
+		// issuer lets the pipe drain between tiles.  With two issuers one warp does its waits while
+		// the other warp's MMAs execute.  Tiles are independent (own TMEM stage, own halo stage);
+		// only the resident weights couple them, see `pos` below.
+		const int mi = warp == 1 ? 0 : 1;
 		const uint32_t idesc = make_idesc(64);
 		const uint32_t a_hi = static_cast<uint32_t>(make_smem_desc(0, 1280u, 0) >> 32);
 		const uint32_t b_hi = static_cast<uint32_t>(make_smem_desc(0, 1024u, 0) >> 32);
 		const uint32_t lo_flags = 1u << 16;
+		// tiles of this CTA per layer
+		const int cnt = (p.total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+		                static_cast<int>(gridDim.x);
 		int it = 0;
+		constexpr int kTrace = 64;
+		long long tr0[kTrace], tr1[kTrace], tr2[kTrace];
+		const bool trace = (p.ablate & 16) && (blockIdx.x == 5 || blockIdx.x == 70 || blockIdx.x == 131 || blockIdx.x == 140);
 		for (int l = 0; l < p.n_layers; ++l) {
-			bool first = true;
-			for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+			for (int pos = 0; pos < cnt; ++pos, ++it) {
+				if ((it & 1) != mi) continue;
 				const int as = it % kAccStages;
 				const uint32_t aph = (it / kAccStages) & 1;
-				mbar_wait(tempty_bar(as), aph ^ 1u, p.error_flag, 3);
+				if (trace && it < kTrace) tr0[it] = gtime();
 				const int s = it % p.stages;
 				const uint32_t ph = (it / p.stages) & 1;
+				mbar_wait(tempty_bar(as), aph ^ 1u, p.error_flag, 3);
 				mbar_wait(full_bar(s), ph, p.error_flag, 4);
 				tcgen05_fence_after();
+				if (trace && it < kTrace) tr1[it] = gtime();
 				const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * 64);
 				const uint32_t a_lo = lo_flags | ((smem_base + s * kARegion) >> 4);
 				const uint32_t b_lo = lo_flags | (resb_base >> 4);
-				const bool last = tile + static_cast<int>(gridDim.x) >= p.total_tiles;
+				// the first two tiles of a layer (one per issuer) wait tap by tap for the new weights;
+				// the last two release the slices tap by tap (wempty_tap counts 2 arrivals)
+				const bool fresh = pos < 2;
+				const int releases = pos + 2 >= cnt ? (cnt == 1 ? 2 : 1) : 0;
 				if (elect_one_sync()) {
 #pragma unroll
 					for (int tap = 0; tap < 9; ++tap) {
-						// first tile of a layer: this tap's slice of the new weights must have landed
-						if (first) mbar_wait(wfull_tap(tap), static_cast<uint32_t>(l & 1), p.error_flag, 2);
+						if (fresh) mbar_wait(wfull_tap(tap), static_cast<uint32_t>(l & 1), p.error_flag, 2);
 						const uint32_t a_tap = a_lo + (tap / 3) * 80u + (tap % 3) * 8u;
 						const uint32_t b_tap = b_lo + tap * (kBSlice >> 4);
 #pragma unroll
@@ -297,14 +353,20 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 							const uint64_t b_desc = (static_cast<uint64_t>(b_hi) << 32) | (b_tap + k16 * 2u);
 							umma_f16(d_tmem, a_desc, b_desc, idesc, (tap | k16) != 0 ? 1u : 0u);
 						}
-						// last tile of a layer: this tap's slice may be overwritten once these MMAs retire
-						if (last) umma_commit(wempty_tap(tap));
+						// this tap's slice may be overwritten once these MMAs (of both issuers) retire
+						if (releases >= 1) umma_commit(wempty_tap(tap));
+						if (releases == 2) umma_commit(wempty_tap(tap));
 					}
 					umma_commit(empty_bar(s));
 					umma_commit(tfull_bar(as));
 				}
 				__syncwarp();
-				first = false;
+				if (trace && it < kTrace) tr2[it] = gtime();
+			}
+		}
+		if (trace && lane == 0) {
+			for (int i = mi; i < kTrace && i < it; i += 2) {
+				printf("C%d MMA %d t0 %lld start %lld end %lld\n", (int)blockIdx.x, i, tr0[i] % 100000000, tr1[i] % 100000000, tr2[i] % 100000000);
 			}
 		}
 	} else {
@@ -317,6 +379,9 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 		const int coff = half * 4;
 		if (p.pdl) grid_dependency_wait();
 		int it = 0;
+		constexpr int kTraceE = 64;
+		long long te0[kTraceE], te1[kTraceE], te2[kTraceE];
+		const bool trace = (p.ablate & 16) && (blockIdx.x == 5 || blockIdx.x == 70 || blockIdx.x == 131 || blockIdx.x == 140) && warp == 2;
 		for (int l = 0; l < p.n_layers; ++l) {
 			float bias_reg[32];
 #pragma unroll
@@ -326,14 +391,14 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 			for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
 				const int as = it % kAccStages;
 				const uint32_t aph = (it / kAccStages) & 1;
-				const int ss = it & 1;  // staging tile
-				const uint32_t sph = (it >> 1) & 1;
+				const int ss = it % kStoreWarps;  // staging tile
+				const uint32_t sph = (it / kStoreWarps) & 1;
 				// The shortcut row comes straight from global memory (L2) and never touches shared
 				// memory, whose port the MMA operand fetch saturates.  It was stored two layers ago
 				// by this CTA's own TMA stores; requested before the accumulator wait, so the
 				// latency hides behind the MMAs of this tile.
 				uint4 res[4];
-				if (has_res) {
+				if (has_res && !(p.ablate & 8)) {
 					int b, y0, x0;
 					decode(tile, b, y0, x0);
 					const int y = y0 + (row >> 3), x = x0 + (row & 7);
@@ -346,7 +411,9 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 						res[0] = res[1] = res[2] = res[3] = make_uint4(0u, 0u, 0u, 0u);
 					}
 				}
+				if (trace && it < kTraceE) te0[it] = gtime();
 				mbar_wait(tfull_bar(as), aph, p.error_flag, 5);
+				if (trace && it < kTraceE) te1[it] = gtime();
 				tcgen05_fence_after();
 				uint32_t acc[32];
 				const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
@@ -358,6 +425,12 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 				__syncwarp();
 				if (lane == 0) mbar_arrive(tempty_bar(as));
 				mbar_wait(sfree_bar(ss), sph ^ 1u, p.error_flag, 11);  // staging[ss] consumed by the store of tile it-2
+				if (p.ablate & 1) {
+					if (acc[0] == 0x7fc12345u && res[0].x == 0x12345u) p.flags[0] = 1;
+					__syncwarp();
+					if (lane == 0) mbar_arrive(sready_bar(ss));
+					continue;
+				}
 				float v[32];
 #pragma unroll
 				for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(acc[c]) + bias_reg[c];
@@ -396,6 +469,12 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 				__syncwarp();
 				if (lane == 0) mbar_arrive(sready_bar(ss));
+				if (trace && it < kTraceE) te2[it] = gtime();
+			}
+		}
+		if (trace && lane == 0) {
+			for (int i = 0; i < kTraceE && i < it; ++i) {
+				printf("C%d EPI %d t0 %lld tfull %lld done %lld\n", (int)blockIdx.x, i, te0[i] % 100000000, te1[i] % 100000000, te2[i] % 100000000);
 			}
 		}
 	}
@@ -427,7 +506,7 @@ EncodeTiledFn encodeTiledDF() {
 	return fn;
 }
 
-constexpr uint32_t kFixed = 1024u + 768u + kBBytes + 2u * kEpiTile;  // alignment slack, barriers, weights, staging
+constexpr uint32_t kFixed = 1024u + 768u + kBBytes + kStoreWarps * kEpiTile;  // alignment slack, barriers, weights, staging
 
 }  // namespace
 
@@ -454,6 +533,7 @@ cudaError_t trunk_df_tc_prepare(const TrunkArgs &a, TrunkTcLaunch *out) {
 	if (!a.flags) return cudaErrorInvalidValue;
 	for (int i = 0; i < 3; ++i) p.buffers[i] = static_cast<const __half *>(a.buffers[i]);
 	p.cstride = a.cstride;
+	if (const char *e = std::getenv("JU_TRUNK_ABLATE")) p.ablate = std::atoi(e);
 	int stages = static_cast<int>((kSmemLimit - kFixed) / kARegion);
 	if (stages > kMaxStages) stages = kMaxStages;
 	if (stages < 2) return cudaErrorInvalidValue;
