@@ -2,20 +2,33 @@
 // layers of the generator's residual stack - scripts/training/models.py:193-254,
 // 544-550 - in one launch), but without any grid-wide barrier.
 //
-// A tile of layer l only needs the 3x3 tile neighbourhood of layer l-1.  With the
-// static tile->CTA striding (tile = cta + k*grid) all CTAs advance in waves k, and
-// the neighbours of a wave-k tile lie in waves k-1..k+1, so the dependency is kept
-// per (layer, wave): every completed TMA store bumps a counter (release), and the
-// TMA producer needs counter[l-1][k+1] to be full (acquire) before it requests a
-// halo of layer l, wave k - one cached poll per wave instead of a grid barrier.
-// Wave 0 of layer l+1 only needs waves 0..1 of layer l, which were stored almost a
-// whole layer earlier: in steady state no CTA waits at a layer boundary and the
-// producer prefetches halos of layer l+1 while the MMAs of layer l still run.
+// Dependencies.  A tile of layer l only needs the 3x3 tile neighbourhood of layer
+// l-1.  With the static tile->CTA striding (tile = cta + k*grid) all CTAs advance
+// in waves k, and the neighbours of a wave-k tile lie in waves k-1..k+1, so the
+// dependency is kept per (layer, wave): every completed TMA store bumps a counter
+// (release), and a TMA producer needs counter[l-1][<= k+1] to be full (relaxed
+// spin, then one acquire) before it requests a halo of layer l, wave k.  The
+// needed wave was stored ~6 tile periods earlier, so in steady state nobody waits
+// at a layer boundary and halos of layer l+1 are prefetched while layer l runs.
+// (Exact per-tile flags - 9 acquire polls per tile - were measured slower.)
 //
-// The resident weights are swapped tap by tap: on a CTA's last tile of layer l the
-// MMA warp commits one barrier per tap, a dedicated loader warp refills that tap's
-// 8 KB slice with layer l+1 immediately, and the first tile of layer l+1 waits per
-// tap - the 72 KB reload hides behind the last tile's own MMAs.
+// Warp roles (16 warps, 1 CTA/SM).  Every mbarrier operation has to get through
+// the shared-memory pipe that the UMMA operand fetch saturates (~300 cycles per
+// round trip, measured with an in-kernel timeline), and the tensor pipe only
+// queues ~4 MMAs, so every serial per-tile chain is split over warps that take
+// tiles round-robin:
+//   2 TMA producers   (wait stage-empty, poll wave counters, request the halo)
+//   2 MMA issuers     (their barrier waits overlap the other warp's MMAs)
+//   8 epilogue warps  (TMEM -> regs, +bias, +shortcut, act, fp16 -> staging tile)
+//   3 store warps     (TMA store, wait for completion, GPU-scope publish ~1 us)
+//   1 weight loader
+// The shortcut (ResBlock input) is read straight from L2 with 256-bit loads by
+// the epilogue threads, requested before the accumulator wait.
+//
+// Weights.  The resident 72 KB are swapped tap by tap: the last two tiles of a
+// layer (one per issuer) commit one barrier per tap, the loader warp refills that
+// tap's 8 KB slice with layer l+1 immediately, and the first two tiles of layer
+// l+1 wait per tap - the reload hides behind the last tiles' own MMAs.
 //
 // Buffer reuse is safe without extra dependencies: a buffer is rewritten two
 // layers after it was read, and the read-after-write chain of the writer
@@ -24,8 +37,6 @@
 // Counters are never reset: launch number `epoch` (kept in global memory, advanced
 // by the last CTA to finish) expects (epoch+1) * tiles_in_wave, compared wrap-safe,
 // so the captured CUDA graph replays without any memset node.
-#include <cstdio>
-#include <cstdlib>
 #include <cstring>
 
 #include "kernels.h"
@@ -65,7 +76,6 @@ struct TrunkParams {
 	int *error_flag;
 	const __half *buffers[3];     // T0, T1, T2 (residual rows are read straight from global memory)
 	int cstride;
-	int ablate;  // timing experiments only (JU_TRUNK_ABLATE bit mask); results are wrong when non-zero
 };
 
 struct TrunkMaps {
@@ -80,12 +90,6 @@ __device__ __forceinline__ void ld_global_256(const __half *p, uint4 &a, uint4 &
 	             : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
 	             : "l"(p)
 	             : "memory");
-}
-
-__device__ __forceinline__ long long gtime() {
-	unsigned long long t;
-	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-	return static_cast<long long>(t);
 }
 
 __device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int *p) {
@@ -147,8 +151,6 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 		             : "memory");
 		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 	}
-	long long &t_base = *reinterpret_cast<long long *>(smem_gen + (bar_base - smem_base) + 8u * (2 * kMaxStages + 9));
-	if (threadIdx.x == 0) t_base = gtime();
 	tcgen05_fence_before();
 	__syncthreads();
 	tcgen05_fence_after();
@@ -180,9 +182,6 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 		// ===================== TMA producer (warp converged; lanes 0..8 poll neighbour flags) =====
 		if (p.pdl) grid_dependency_wait();
 		int it = 0;
-		constexpr int kTraceP = 64;
-		long long tp0[kTraceP], tp1[kTraceP], tp2[kTraceP];
-		const bool trace = (p.ablate & 16) && (blockIdx.x == 5 || blockIdx.x == 70 || blockIdx.x == 131 || blockIdx.x == 140);
 		for (int l = 0; l < p.n_layers; ++l) {
 			const CUtensorMap *min = &maps.in[layer_in(l)];
 			int known = -1;  // highest wave of layer l-1 known to be completely stored
@@ -192,31 +191,34 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 				if ((it & 1) != pme) continue;
 				const int s = it % p.stages;
 				const uint32_t ph = (it / p.stages) & 1;
-				if (trace && it < kTraceP) tp0[it] = gtime();
 				mbar_wait(empty_bar(s), ph ^ 1u, p.error_flag, 1);
-				if (trace && it < kTraceP) tp1[it] = gtime();
 				bool polled = false;
 				if (l > 0) {
 					// waves <= k+1 of layer l-1 must be completely stored (covers the 3x3 neighbourhood)
 					const int k = (tile - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x);
 					const int needw = k + wave_reach < n_waves ? k + wave_reach : n_waves - 1;
 					while (known < needw) {
-						const int wv = known + 1;
-						const int cnt = wv + 1 < n_waves ? static_cast<int>(gridDim.x)
-						                                 : p.total_tiles - wv * static_cast<int>(gridDim.x);
-						const unsigned int target = (epoch + 1u) * static_cast<unsigned int>(cnt);
-						const unsigned int *ctr = p.flags + (l - 1) * n_waves + wv;
-						// spin on relaxed loads (no L1 invalidation per poll), then acquire once
+						// lane i polls wave known+1+i: relaxed spins (no L1 invalidation per poll), then one
+						// acquire load per counter once all of them are complete
+						const int wv = known + 1 + lane;
+						const bool mine = wv <= needw;
+						const int cntw = wv + 1 < n_waves ? static_cast<int>(gridDim.x)
+						                                  : p.total_tiles - wv * static_cast<int>(gridDim.x);
+						const unsigned int target = (epoch + 1u) * static_cast<unsigned int>(cntw);
+						const unsigned int *ctr = p.flags + (l - 1) * n_waves + (mine ? wv : 0);
 						unsigned int spins = 0;
-						while (static_cast<int>(ld_relaxed_gpu(ctr) - target) < 0) {
+						while (true) {
+							const bool ok = !mine || static_cast<int>(ld_relaxed_gpu(ctr) - target) >= 0;
+							if (__all_sync(0xffffffffu, ok)) break;
 							__nanosleep(32);
 							if (++spins > (1u << 24)) {
 								if (p.error_flag) atomicExch(p.error_flag, 8);
 								__trap();
 							}
 						}
-						(void)ld_acquire_gpu(ctr);
-						known = wv;
+						if (mine) (void)ld_acquire_gpu(ctr);
+						__syncwarp();
+						known = known + 32 < needw ? known + 32 : needw;
 						polled = true;
 					}
 				}
@@ -225,21 +227,10 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 						// order the async-proxy (TMA) reads below after the acquire loads above
 						asm volatile("fence.proxy.async;" ::: "memory");
 					}
-					if (p.ablate & 4) {
-						mbar_arrive(full_bar(s));
-					} else {
-						mbar_arrive_expect_tx(full_bar(s), kABox);
-						tma_load_4d(smem_base + s * kARegion, min, full_bar(s), 0, x0 - 1, y0 - 1, b);
-					}
+					mbar_arrive_expect_tx(full_bar(s), kABox);
+					tma_load_4d(smem_base + s * kARegion, min, full_bar(s), 0, x0 - 1, y0 - 1, b);
 				}
 				__syncwarp();
-				if (trace && it < kTraceP) tp2[it] = gtime();
-			}
-		}
-		if (trace && lane == 0) {
-			for (int i = 0; i < kTraceP && i < it; ++i) {
-				if ((i & 1) != pme) continue;
-				printf("C%d PRO %d t0 %lld empty %lld issued %lld\n", (int)blockIdx.x, i, tp0[i] % 100000000, tp1[i] % 100000000, tp2[i] % 100000000);
 			}
 		}
 	} else if (warp == 10) {
@@ -262,9 +253,6 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 			if (p.pdl) grid_dependency_wait();
 			const int me = warp - 11;
 			int it = 0;
-			constexpr int kTraceS = 64;
-			long long ts0[kTraceS], ts1[kTraceS], ts2[kTraceS];
-			const bool trace = (p.ablate & 16) && (blockIdx.x == 5 || blockIdx.x == 70 || blockIdx.x == 131 || blockIdx.x == 140) && me == 0;
 			for (int l = 0; l < p.n_layers; ++l) {
 				const CUtensorMap *mout = &maps.tile[layer_out(l)];
 				for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
@@ -274,11 +262,9 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 					const int as = me;  // this warp's staging tile
 					const uint32_t aph = (it / kStoreWarps) & 1;
 					mbar_wait(sready_bar(as), aph, p.error_flag, 10);
-					if (trace && it < kTraceS) ts0[it] = gtime();
-					if (!(p.ablate & 2)) tma_store_4d(mout, epi_out_base + as * kEpiTile, 0, x0, y0, b);
+					tma_store_4d(mout, epi_out_base + as * kEpiTile, 0, x0, y0, b);
 					asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem tile consumed
 					mbar_arrive(sfree_bar(as));
-					if (trace && it < kTraceS) ts1[it] = gtime();
 					asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // global writes complete
 					// the bulk store has completed (async proxy): order it before the generic-proxy
 					// release below, which makes it visible to every acquiring producer warp
@@ -287,12 +273,6 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 					                 p.flags + l * n_waves +
 					                 (tile - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x))
 					             : "memory");
-					if (trace && it < kTraceS) ts2[it] = gtime();
-				}
-			}
-			if (trace) {
-				for (int i = 0; i < kTraceS && i < it; i += kStoreWarps) {
-					printf("C%d STO %d sready %lld sfree %lld published %lld\n", (int)blockIdx.x, i, ts0[i] % 100000000, ts1[i] % 100000000, ts2[i] % 100000000);
 				}
 			}
 			__threadfence();
@@ -319,21 +299,16 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 		const int cnt = (p.total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
 		                static_cast<int>(gridDim.x);
 		int it = 0;
-		constexpr int kTrace = 64;
-		long long tr0[kTrace], tr1[kTrace], tr2[kTrace];
-		const bool trace = (p.ablate & 16) && (blockIdx.x == 5 || blockIdx.x == 70 || blockIdx.x == 131 || blockIdx.x == 140);
 		for (int l = 0; l < p.n_layers; ++l) {
 			for (int pos = 0; pos < cnt; ++pos, ++it) {
 				if ((it & 1) != mi) continue;
 				const int as = it % kAccStages;
 				const uint32_t aph = (it / kAccStages) & 1;
-				if (trace && it < kTrace) tr0[it] = gtime();
 				const int s = it % p.stages;
 				const uint32_t ph = (it / p.stages) & 1;
 				mbar_wait(tempty_bar(as), aph ^ 1u, p.error_flag, 3);
 				mbar_wait(full_bar(s), ph, p.error_flag, 4);
 				tcgen05_fence_after();
-				if (trace && it < kTrace) tr1[it] = gtime();
 				const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * 64);
 				const uint32_t a_lo = lo_flags | ((smem_base + s * kARegion) >> 4);
 				const uint32_t b_lo = lo_flags | (resb_base >> 4);
@@ -361,12 +336,6 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 					umma_commit(tfull_bar(as));
 				}
 				__syncwarp();
-				if (trace && it < kTrace) tr2[it] = gtime();
-			}
-		}
-		if (trace && lane == 0) {
-			for (int i = mi; i < kTrace && i < it; i += 2) {
-				printf("C%d MMA %d t0 %lld start %lld end %lld\n", (int)blockIdx.x, i, tr0[i] % 100000000, tr1[i] % 100000000, tr2[i] % 100000000);
 			}
 		}
 	} else {
@@ -379,9 +348,6 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 		const int coff = half * 4;
 		if (p.pdl) grid_dependency_wait();
 		int it = 0;
-		constexpr int kTraceE = 64;
-		long long te0[kTraceE], te1[kTraceE], te2[kTraceE];
-		const bool trace = (p.ablate & 16) && (blockIdx.x == 5 || blockIdx.x == 70 || blockIdx.x == 131 || blockIdx.x == 140) && warp == 2;
 		for (int l = 0; l < p.n_layers; ++l) {
 			float bias_reg[32];
 #pragma unroll
@@ -398,7 +364,7 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 				// by this CTA's own TMA stores; requested before the accumulator wait, so the
 				// latency hides behind the MMAs of this tile.
 				uint4 res[4];
-				if (has_res && !(p.ablate & 8)) {
+				if (has_res) {
 					int b, y0, x0;
 					decode(tile, b, y0, x0);
 					const int y = y0 + (row >> 3), x = x0 + (row & 7);
@@ -411,9 +377,7 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 						res[0] = res[1] = res[2] = res[3] = make_uint4(0u, 0u, 0u, 0u);
 					}
 				}
-				if (trace && it < kTraceE) te0[it] = gtime();
 				mbar_wait(tfull_bar(as), aph, p.error_flag, 5);
-				if (trace && it < kTraceE) te1[it] = gtime();
 				tcgen05_fence_after();
 				uint32_t acc[32];
 				const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
@@ -425,12 +389,6 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 				__syncwarp();
 				if (lane == 0) mbar_arrive(tempty_bar(as));
 				mbar_wait(sfree_bar(ss), sph ^ 1u, p.error_flag, 11);  // staging[ss] consumed by the store of tile it-2
-				if (p.ablate & 1) {
-					if (acc[0] == 0x7fc12345u && res[0].x == 0x12345u) p.flags[0] = 1;
-					__syncwarp();
-					if (lane == 0) mbar_arrive(sready_bar(ss));
-					continue;
-				}
 				float v[32];
 #pragma unroll
 				for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(acc[c]) + bias_reg[c];
@@ -469,12 +427,6 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 				__syncwarp();
 				if (lane == 0) mbar_arrive(sready_bar(ss));
-				if (trace && it < kTraceE) te2[it] = gtime();
-			}
-		}
-		if (trace && lane == 0) {
-			for (int i = 0; i < kTraceE && i < it; ++i) {
-				printf("C%d EPI %d t0 %lld tfull %lld done %lld\n", (int)blockIdx.x, i, te0[i] % 100000000, te1[i] % 100000000, te2[i] % 100000000);
 			}
 		}
 	}
@@ -533,7 +485,6 @@ cudaError_t trunk_df_tc_prepare(const TrunkArgs &a, TrunkTcLaunch *out) {
 	if (!a.flags) return cudaErrorInvalidValue;
 	for (int i = 0; i < 3; ++i) p.buffers[i] = static_cast<const __half *>(a.buffers[i]);
 	p.cstride = a.cstride;
-	if (const char *e = std::getenv("JU_TRUNK_ABLATE")) p.ablate = std::atoi(e);
 	int stages = static_cast<int>((kSmemLimit - kFixed) / kARegion);
 	if (stages > kMaxStages) stages = kMaxStages;
 	if (stages < 2) return cudaErrorInvalidValue;
