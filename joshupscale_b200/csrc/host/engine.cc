@@ -436,7 +436,7 @@ void Engine::buildPlan(int parity) {
 			const std::size_t per = conv_tc_weight_bytes(3, 64, 64);
 			m_TrunkWeights = DeviceBuffer(per * nLayers);
 			m_TrunkBias = DeviceBuffer(sizeof(float) * 64 * nLayers);
-			m_TrunkCounter = DeviceBuffer(sizeof(unsigned int) * 2);
+			m_TrunkCounter = DeviceBuffer(sizeof(unsigned int) * 2 * static_cast<std::size_t>(B));
 			m_TrunkFlags = DeviceBuffer(sizeof(unsigned int) * static_cast<std::size_t>(nLayers) * B * ((H + 15) / 16) * ((W + 7) / 8));
 			for (int l = 0; l < nLayers; ++l) {
 				ConvLayer *L = layer("generator/block_" + std::to_string(l / 2 + 1) + "/conv_" + std::to_string(l % 2 + 1));
@@ -464,14 +464,29 @@ void Engine::buildPlan(int parity) {
 		ta.n_layers = nLayers;
 		ta.act = first->act;
 		ta.slope = first->slope;
-		TrunkTcLaunch launch;
 		// JU_TRUNK_SYNC: 1 = per-wave dataflow counters (trunk_df_tc.cu), 0 = grid barrier per layer
-		// (trunk_tc.cu), -1 (default) = dataflow for short layers (few tile waves per CTA, where the
-		// barrier bubble matters) and the barrier for large batches, which it keeps L2-coherent
+		// (trunk_tc.cu), -1 (default) = dataflow.
+		// JU_TRUNK_SUBBATCH (default 2): with the dataflow trunk a large batch runs as consecutive
+		// launches of this many streams, each through ALL layers: three trunk tensors of 2 PSP streams
+		// (100 MB) stay resident in the 126 MB L2, while one launch over 16 streams streams ~800 MB per
+		// layer through HBM.  0 = one launch for the whole batch.
 		const int syncMode = envInt("JU_TRUNK_SYNC", -1);
-		const int tileWaves = (B * ((H + 15) / 16) * ((W + 7) / 8) + m_SmCount - 1) / m_SmCount;
-		const bool dataflow = syncMode < 0 ? tileWaves <= envInt("JU_TRUNK_DF_MAX_WAVES", 8) : syncMode != 0;
-		checkCuda(dataflow ? trunk_df_tc_prepare(ta, &launch) : trunk_tc_prepare(ta, &launch), "trunk_tc_prepare");
+		const bool dataflow = syncMode != 0;
+		int chunk = dataflow ? envInt("JU_TRUNK_SUBBATCH", 2) : 0;
+		if (chunk <= 0 || chunk > B) chunk = B;
+		const std::size_t perStream = static_cast<std::size_t>(H) * W * gs;
+		const std::size_t tilesPerStream = static_cast<std::size_t>((H + 15) / 16) * ((W + 7) / 8);
+		std::vector<TrunkTcLaunch> launches;
+		for (int b0 = 0; b0 < B; b0 += chunk) {
+			TrunkArgs sub = ta;
+			sub.batch = std::min(chunk, B - b0);
+			for (int i = 0; i < 3; ++i) sub.buffers[i] = static_cast<__half *>(ta.buffers[i]) + perStream * b0;
+			sub.sync_counter = ta.sync_counter + 2 * (b0 / chunk);
+			sub.flags = ta.flags + static_cast<std::size_t>(nLayers) * tilesPerStream * b0;
+			TrunkTcLaunch launch;
+			checkCuda(dataflow ? trunk_df_tc_prepare(sub, &launch) : trunk_tc_prepare(sub, &launch), "trunk_tc_prepare");
+			launches.push_back(launch);
+		}
 		Op op;
 		op.name = "generator/block_*(persistent)";
 		op.tensorBound = true;
@@ -479,11 +494,13 @@ void Engine::buildPlan(int parity) {
 		op.flops = 2.0 * B * H * W * 9.0 * 64 * 64 * nLayers;
 		op.bytes = static_cast<double>(B) * H * W * 64 * 2.0 * (2.0 * nLayers + 0.5 * nLayers);
 		int *err = m_TcError.as<int>();
-		if (dataflow) {
-			op.run = [launch, err](cudaStream_t st) { return trunk_df_tc_launch(launch, err, st); };
-		} else {
-			op.run = [launch, err](cudaStream_t st) { return trunk_tc_launch(launch, err, st); };
-		}
+		op.run = [launches, err, dataflow](cudaStream_t st) {
+			for (const TrunkTcLaunch &l : launches) {
+				cudaError_t e = dataflow ? trunk_df_tc_launch(l, err, st) : trunk_tc_launch(l, err, st);
+				if (e != cudaSuccess) return e;
+			}
+			return cudaSuccess;
+		};
 		plan.push_back(std::move(op));
 		++m_TcOps;
 		cur = trunk_output_buffer(nLayers) == 0 ? t0 : t2;
