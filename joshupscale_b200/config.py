@@ -119,6 +119,31 @@ class ModelConfig:
         return 2.0 * (self.flow_gmacs() + self.gen_gmacs())
 
 
+@dataclasses.dataclass(frozen=True)
+class OutputFilter:
+    """Output temporal filter + scene-cut gate that the reference bakes into the
+    exported graph; fields and defaults are the CLI arguments of
+    scripts/inference/onnx/frame_moving_avg.py:53-87.  Stored in the model
+    container as the float32[8] tensor `meta/frame_moving_avg`
+    (weights.with_output_filter) and executed by csrc/kernels/frame_filter.cu."""
+    strength: float = 0.25
+    window: int = 0  # scene detection window in output pixels, 0 = global
+    threshold: float = 0.1
+    gain: float = 0.0  # 0 = sign function, otherwise tanh(gain * ...)
+    norm: str = "l1"  # "l1" | "l2"
+    limit: bool = False  # clip the warped previous output to [-0.5, 0.5] first
+    luma_normalize: bool = False
+
+    def as_vector(self):
+        if self.norm.lower() not in ("l1", "l2"):
+            raise ValueError(f"unknown norm {self.norm}")
+        if self.window < 0:
+            raise ValueError("window must be >= 0")
+        return [1.0, float(self.strength), float(self.window), float(self.threshold), float(self.gain),
+                1.0 if self.norm.lower() == "l2" else 0.0, 1.0 if self.limit else 0.0,
+                1.0 if self.luma_normalize else 0.0]
+
+
 def preset(name: str) -> ModelConfig:
     """Named configurations."""
     presets = {

@@ -46,6 +46,25 @@ Engine::Engine(const ModelFile &model, int device, int batch)
 	JU_CUDA(cudaStreamCreateWithFlags(&m_Stream, cudaStreamNonBlocking));
 	try {
 		buildLayers(model);
+		if (model.has("meta/frame_moving_avg")) {
+			// output temporal filter baked into the model file, like the reference bakes it into the
+			// exported graph (scripts/inference/onnx/frame_moving_avg.py); float32[8] =
+			// {enabled, strength, window, threshold, gain, norm (0 L1 / 1 L2), limit, luma_normalize}
+			const HostTensor &t = model.tensor("meta/frame_moving_avg");
+			if (t.data.size() < 8) throw ModelException("meta/frame_moving_avg must hold 8 values");
+			if (t.data[0] != 0.f) {
+				m_FilterOn = true;
+				m_Filter.strength = t.data[1];
+				m_Filter.window = static_cast<int>(t.data[2]);
+				m_Filter.threshold = t.data[3];
+				m_Filter.gain = t.data[4];
+				m_Filter.norm_l2 = t.data[5] != 0.f;
+				m_Filter.limit = t.data[6] != 0.f;
+				m_Filter.luma = t.data[7] != 0.f;
+				m_Filter.c3 = static_cast<float>(1.0 - static_cast<double>(t.data[1]) / 2.0);
+				if (m_Filter.window < 0) throw ModelException("frame_moving_avg window must be >= 0");
+			}
+		}
 		allocate();
 		buildPlan(0);
 		buildPlan(1);
@@ -204,6 +223,14 @@ void Engine::allocate() {
 	m_GenIn = DeviceBuffer(B * H * W * 64 * sizeof(__half));
 	for (auto &t : m_Trunk) t = DeviceBuffer(B * H * W * gstride * sizeof(__half));
 	m_Mid = DeviceBuffer(B * 4 * H * W * 32 * sizeof(__half));
+	if (m_FilterOn) {
+		m_OutRaw = DeviceBuffer(B * 16 * H * W * 4 * sizeof(__half));
+		int cy, cx, pt, pl;
+		filter_geometry(m_Filter, static_cast<int>(H), static_cast<int>(W), &cy, &cx, &pt, &pl);
+		const std::size_t work = std::max<std::size_t>(
+		    filter_partials_per_stream(static_cast<int>(H), static_cast<int>(W)), static_cast<std::size_t>(cy) * cx);
+		m_FilterScratch = DeviceBuffer(B * (1 + work) * sizeof(float));
+	}
 
 	registerTensor("flow_in", m_FlowIn[0].get(), m_FlowIn[1].get(), 1,
 	    {B, PH, PW, static_cast<std::uint64_t>(m_FlowCStride)}, m_FlowIn[0].bytes(), true);
@@ -531,9 +558,9 @@ void Engine::buildPlan(int parity) {
 		ta.w2 = m_W2.as<float>();
 		ta.bias2 = m_B2.as<float>();
 		ta.io = io;
-		ta.pre_gen_next = preGenNext;
+		ta.pre_gen_next = m_FilterOn ? m_OutRaw.as<__half>() : preGenNext;
 		ta.out_raw = nullptr;
-		ta.brightness = bright;
+		ta.brightness = m_FilterOn ? nullptr : bright;
 		ta.batch = B;
 		ta.h = H;
 		ta.w = W;
@@ -552,6 +579,7 @@ void Engine::buildPlan(int parity) {
 		op.run = [launch, err](cudaStream_t st) { return tail_tc_launch(launch, err, st); };
 		plan.push_back(std::move(op));
 		++m_TcOps;
+		if (m_FilterOn) plan.push_back(filterOp(io, preGenNext, bright));
 		return;
 	}
 	plan.push_back(convOp(ct1, cur, gs, nullptr, m_Mid.get(), 32, H, W, false));
@@ -563,11 +591,33 @@ void Engine::buildPlan(int parity) {
 		// read mid (32ch fp16 @2Hx2W) + LR input + write BGRX u8 + fp16 state (3ch), SURVEY 8(d)
 		op.bytes = static_cast<double>(B) * (4.0 * H * W * 32 * 2 + H * W * 4.0 + 16.0 * H * W * (4 + 3 * 2));
 		op.flops = 2.0 * B * 4.0 * H * W * 32 * 12;
+		__half *stateOut = m_FilterOn ? m_OutRaw.as<__half>() : preGenNext;
+		const float *stateBright = m_FilterOn ? nullptr : bright;
 		op.run = [=](cudaStream_t st) {
-			return launch_final(mid, w2, b2, io, preGenNext, nullptr, bright, B, H, W, st);
+			return launch_final(mid, w2, b2, io, stateOut, nullptr, stateBright, B, H, W, st);
 		};
 		plan.push_back(std::move(op));
 	}
+	if (m_FilterOn) plan.push_back(filterOp(io, preGenNext, bright));
+}
+
+// frame_moving_avg.py:142-307: blend the generator output (left in m_OutRaw by the tail kernel,
+// un-normalised) with the warped previous output still sitting in the generator input tensor;
+// rewrites the u8 image and produces the recurrent state
+Op Engine::filterOp(const FrameIO *io, __half *preGenNext, const float *bright) {
+	const int B = m_Batch, H = m_Spec.frameH, W = m_Spec.frameW;
+	Op op;
+	op.name = "frame_moving_avg";
+	// two passes over out (4 x fp16) and pw (fp16) + u8 image + fp16 state
+	op.bytes = static_cast<double>(B) * (2.0 * (16.0 * H * W * 8 + H * W * 128.0) + 16.0 * H * W * (4 + 8));
+	const __half *outRaw = m_OutRaw.as<__half>();
+	const __half *genIn = m_GenIn.as<__half>();
+	float *scratch = m_FilterScratch.as<float>();
+	const FilterParams fp = m_Filter;
+	op.run = [=](cudaStream_t st) {
+		return launch_frame_filter(outRaw, genIn, io, preGenNext, bright, scratch, fp, B, H, W, st);
+	};
+	return op;
 }
 
 void Engine::capture(int parity) {

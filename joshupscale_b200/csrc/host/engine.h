@@ -81,6 +81,7 @@ private:
 	void buildPlan(int parity);
 	void capture(int parity);
 	ConvLayer *addConv(const std::string &name, const FoldedConv &f, int act, float slope, bool shuffle2);
+	Op filterOp(const FrameIO *io, __half *preGenNext, const float *bright);
 	Op convOp(ConvLayer *layer, const __half *in, int cinStride, const __half *residual, void *out,
 	    int coutStride, int h, int w, bool outF32, bool pool = false);
 	DeviceBuffer &newActivation(std::size_t bytes);
@@ -111,6 +112,9 @@ private:
 
 	DeviceBuffer m_FlowIn[2], m_PreGen[2];
 	DeviceBuffer m_FlowHead, m_GenIn, m_Trunk[3], m_Mid, m_W2, m_B2;
+	bool m_FilterOn = false;
+	FilterParams m_Filter{};
+	DeviceBuffer m_OutRaw, m_FilterScratch;
 	std::vector<std::unique_ptr<DeviceBuffer>> m_Activations;
 	std::vector<std::unique_ptr<ConvLayer>> m_Layers;
 	std::map<std::string, ConvLayer *> m_LayerByName;

@@ -157,4 +157,25 @@ cudaError_t launch_final(const __half *mid, const float *w2, const float *bias2,
     __half *pre_gen_next, float *out_raw, const float *brightness, int batch, int h, int w,
     cudaStream_t s);
 
+// ---- output temporal filter (frame_filter.cu) ------------------------------
+// Parameters of scripts/inference/onnx/frame_moving_avg.py:53-87.
+struct FilterParams {
+	float strength;   // -s
+	float threshold;  // -t
+	float gain;       // -g (0 = sign function)
+	float c3;         // 1 - strength / 2, rounded once on the host like the script's constant
+	int window;       // -w (0 = global mean)
+	int norm_l2;      // -n: 0 = L1, 1 = L2
+	int limit;        // -l
+	int luma;         // --luma-normalize
+};
+void filter_geometry(const FilterParams &fp, int h, int w, int *cells_y, int *cells_x, int *pad_t, int *pad_l);
+int filter_partials_per_stream(int h, int w);
+// out_raw: generator output after Clip [batch, 4h, 4w, 4] fp16; gen_in: generator input [batch, h, w, 64]
+// (warped previous output in channels 3..50); scratch: batch * (1 + max(partials, cells)) floats.
+// Writes the filtered u8 BGRX image (io[b].out) and the recurrent state pre_gen_next.
+cudaError_t launch_frame_filter(const __half *out_raw, const __half *gen_in, const FrameIO *io, __half *pre_gen_next,
+    const float *brightness, float *scratch, const FilterParams &fp, int batch, int h, int w, cudaStream_t s);
+
+
 }  // namespace ju

@@ -158,6 +158,18 @@ def _pack_header(cfg: ModelConfig, n_tensors: int, header_bytes: int) -> bytes:
         int(cfg.normalize_brightness), BN_EPS, n_tensors)
 
 
+FILTER_TENSOR = "meta/frame_moving_avg"
+
+
+def with_output_filter(weights: Dict[str, np.ndarray], flt) -> "OrderedDict[str, np.ndarray]":
+    """Copy of `weights` with the output filter `flt` (config.OutputFilter, or None
+    to remove it) attached as the `meta/frame_moving_avg` tensor."""
+    out = OrderedDict((k, v) for k, v in weights.items() if k != FILTER_TENSOR)
+    if flt is not None:
+        out[FILTER_TENSOR] = np.asarray(flt.as_vector(), np.float32)
+    return out
+
+
 def save_model(path: str, cfg: ModelConfig, weights: Dict[str, np.ndarray]) -> None:
     """Write a `.jup` container: header, tensor table, 64-byte aligned fp32 data."""
     cfg.validate()

@@ -215,10 +215,12 @@ class Graph:
     ModelConfig-like object `cfg` and a dict of Keras-layout weights."""
 
     def __init__(self, cfg, weights: Dict[str, np.ndarray],
-                 precision: str = "fp32"):
+                 precision: str = "fp32", output_filter=None):
         assert precision in ("fp32", "fp16emu")
         self.cfg = cfg
         self.precision = precision
+        # optional oracle.frame_filter.FrameFilter (scripts/inference/onnx/frame_moving_avg.py)
+        self.output_filter = output_filter
         self.w = {k: _t(np.asarray(v, np.float32)) for k, v in weights.items()}
         self.taps: Dict[str, torch.Tensor] = {}
         self.keep_taps = False
@@ -379,6 +381,11 @@ class Graph:
             pre_warp = pre_warp + brightness
         pre_warp = self._round(pre_warp)
         out_raw = self.generator(cur, pre_warp)
+        if self.output_filter is not None:
+            from .frame_filter import frame_moving_avg
+            if self.precision == "fp16emu":
+                out_raw = r16(out_raw)  # the product blends the fp16-stored generator output
+            out_raw = frame_moving_avg(out_raw, pre_warp, self.output_filter)
         output = pack_bgrx(postprocess(out_raw))
         new_pre_gen = out_raw - brightness if brightness is not None else out_raw
         new_state = {
