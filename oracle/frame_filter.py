@@ -76,9 +76,12 @@ def _resize_asymmetric(x: torch.Tensor, scale: int) -> torch.Tensor:
     return top * (1 - ty)[None, :, None] + bot * ty[None, :, None]
 
 
-def frame_moving_avg(out: torch.Tensor, pre_warp: torch.Tensor, flt: FrameFilter) -> torch.Tensor:
+def frame_moving_avg(out: torch.Tensor, pre_warp: torch.Tensor, flt: FrameFilter,
+                     debug: dict = None) -> torch.Tensor:
     """out, pre_warp: float32 [N, 4H, 4W, 3] (NHWC, BGR).  Each batch entry is
-    an independent stream (the reference graph has N = 1)."""
+    an independent stream (the reference graph has N = 1).  `debug`, if given,
+    receives "th": the scene-detection value before sign / tanh ([N] or [N, cells_y,
+    cells_x]) so that tests can tell decisions that sit on the threshold."""
     s = float(flt.strength)
     gain_coef = 1.0 if flt.gain == 0 else float(flt.gain)
     pw = torch.clamp(pre_warp, -0.5, 0.5) if flt.limit else pre_warp
@@ -98,6 +101,8 @@ def frame_moving_avg(out: torch.Tensor, pre_warp: torch.Tensor, flt: FrameFilter
             if flt.gain != 0:
                 m = m * np.float32(gain_coef)
         th = m + np.float32(-flt.threshold * gain_coef)
+        if debug is not None:
+            debug["th"] = th.clone()
         cond = torch.sign(th) if flt.gain == 0 else torch.tanh(th)
         cond = cond.view(n, 1, 1, 1)
     else:
@@ -111,6 +116,9 @@ def frame_moving_avg(out: torch.Tensor, pre_warp: torch.Tensor, flt: FrameFilter
         dn = F.pad(dn, (pad_l, ow - ww - pad_l, pad_t, oh - hh - pad_t))
         m = F.conv2d(dn, kernel, stride=wnd)[:, 0]  # [N, oh/w, ow/w]
         th = m + np.float32(-flt.threshold * gain_coef)
+        if debug is not None:
+            debug["th"] = th.clone()
+            debug["pad"] = (pad_t, pad_l)
         cond = torch.sign(th) if flt.gain == 0 else torch.tanh(th)
         cond = _resize_asymmetric(cond, wnd)[:, pad_t:pad_t + hh, pad_l:pad_l + ww]
         cond = cond.unsqueeze(-1)

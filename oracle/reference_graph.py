@@ -385,7 +385,10 @@ class Graph:
             from .frame_filter import frame_moving_avg
             if self.precision == "fp16emu":
                 out_raw = r16(out_raw)  # the product blends the fp16-stored generator output
-            out_raw = frame_moving_avg(out_raw, pre_warp, self.output_filter)
+            filter_debug = {}
+            out_raw = frame_moving_avg(out_raw, pre_warp, self.output_filter, filter_debug)
+        else:
+            filter_debug = None
         output = pack_bgrx(postprocess(out_raw))
         new_pre_gen = out_raw - brightness if brightness is not None else out_raw
         new_state = {
@@ -393,7 +396,7 @@ class Graph:
             "last_frames": [cur_pad] + list(state["last_frames"][:-1]),
         }
         aux = {"flow": flow, "pre_warp": pre_warp, "out_raw": out_raw,
-               "cur_pad": cur_pad}
+               "cur_pad": cur_pad, "filter": filter_debug}
         return output, new_state, aux
 
     def run(self, frames_u8, state=None):

@@ -30,15 +30,38 @@ def _model(tmp_path, preset, flt, tag):
     return cfg, w, path
 
 
+# thresholds sit between the scene statistics of a steady pan and of a hard cut for these seeded
+# models (L1 mean ~0.22 / 0.27, L2 mean ~0.077 / 0.114), so both branches of the gate are taken
 CASES = [
-    ("small", dict()),                                            # script defaults: global L1, sign
-    ("small", dict(strength=0.5, threshold=0.02, norm="l2", limit=True)),
-    ("small", dict(gain=6.0, luma_normalize=True, threshold=0.05)),
-    ("small", dict(window=16, threshold=0.03)),
-    ("small", dict(window=24, gain=5.0, norm="l2", luma_normalize=True, limit=True, threshold=0.004)),
-    ("tiny", dict(window=7, strength=0.4, threshold=0.02)),       # 7 divides neither 84 nor 108
-    ("small_bright", dict(threshold=0.05)),                        # with brightness normalisation
+    ("small", dict(threshold=0.245)),                              # global L1, sign
+    ("small", dict(strength=0.5, threshold=0.095, norm="l2", limit=True)),
+    ("small", dict(gain=6.0, luma_normalize=True, threshold=0.2)),
+    ("small", dict(window=16, threshold=0.23)),                    # per-cell sign decisions
+    ("small", dict(window=24, gain=5.0, norm="l2", luma_normalize=True, limit=True, threshold=0.08)),
+    ("tiny", dict(window=7, strength=0.4, threshold=0.21)),        # 7 divides neither 84 nor 108
+    ("small_bright", dict(threshold=0.27)),                        # with brightness normalisation
 ]
+
+
+def _undecided_mask(cfg, flt, dbg, margin=2e-3):
+    """Pixels whose gate value depends on a sign() decision that sits within `margin` of the
+    threshold in the oracle: fp16 storage may legitimately flip those (the function is
+    discontinuous there), so they are excluded from the comparison."""
+    hh, ww = cfg.out_height, cfg.out_width
+    if flt.gain != 0:
+        return np.zeros((hh, ww), bool)
+    th = dbg["th"][0].numpy()
+    if flt.window == 0:
+        return np.full((hh, ww), bool(abs(th) < margin))
+    near = np.abs(th) < margin
+    # bilinear interpolation spreads a cell over its neighbours: dilate by one cell
+    grown = near.copy()
+    grown[1:] |= near[:-1]; grown[:-1] |= near[1:]
+    g2 = grown.copy()
+    g2[:, 1:] |= grown[:, :-1]; g2[:, :-1] |= grown[:, 1:]
+    pt, pl = dbg["pad"]
+    full = np.kron(g2, np.ones((flt.window, flt.window), bool))
+    return full[pt:pt + hh, pl:pl + ww]
 
 
 @pytest.mark.parametrize("preset,kw", CASES)
@@ -46,20 +69,42 @@ def test_filtered_output_matches_oracle(tmp_path, preset, kw):
     cfg, w, path = _model(tmp_path, preset, jcfg.OutputFilter(**kw), "f")
     # pan with a hard cut in the middle: both branches of the scene gate are taken
     frames = synthetic.frames(cfg.frame_height, cfg.frame_width, 8, kind="cut")
-    with jrt.Runtime(path, 0, 1) as rt:
-        got = np.stack([rt.process(f) for f in frames])
     oflt = ff.FrameFilter(**kw)
-    ref, _ = og.Graph(cfg, w, "fp32", output_filter=oflt).run(frames)
-    emu, _ = og.Graph(cfg, w, "fp16emu", output_filter=oflt).run(frames)
+    # Per-cell sign() decisions are discontinuous: a cell that flips under fp16 storage also changes
+    # the recurrent state under it.  For those cases the GPU state is re-seeded from the fp16 oracle
+    # before every frame, so each frame is compared on its own (cells on the threshold are masked).
+    resync = oflt.window > 0 and oflt.gain == 0
     plain, _ = og.Graph(cfg, w, "fp32").run(frames)
-    assert not got[..., 3].any()
-    # the filter must actually change the picture on this sequence
-    assert (ref[..., :3] != plain[..., :3]).mean() > 0.05
+    gref, gemu = og.Graph(cfg, w, "fp32", output_filter=oflt), og.Graph(cfg, w, "fp16emu", output_filter=oflt)
+    sref, semu = gref.zero_state(1), gemu.zero_state(1)
+    changed = 0.0
+    excluded = 0.0
+    rt = jrt.Runtime(path, 0, 1)
+    got = []
     for t in range(len(frames)):
-        m16, frac16, _ = u8_stats(got[t, ..., :3], emu[t, ..., :3])
-        m32, _, psnr32 = u8_stats(got[t, ..., :3], ref[t, ..., :3])
+        if resync and t > 0:
+            st = np.zeros((1, cfg.out_height, cfg.out_width, 4), np.float16)
+            st[..., :3] = semu["pre_gen"].numpy().astype(np.float16)
+            rt.write_state("pre_gen", st)
+            sref = {"pre_gen": semu["pre_gen"].clone(), "last_frames": [x.clone() for x in semu["last_frames"]]}
+        got.append(rt.process(frames[t]))
+        assert not got[t][..., 3].any()
+        ref, sref, aux = gref.step(frames[t:t + 1], sref)
+        emu, semu, _ = gemu.step(frames[t:t + 1], semu)
+        ref, emu = ref[0].numpy(), emu[0].numpy()
+        keep = ~_undecided_mask(cfg, oflt, aux["filter"])
+        excluded += 1.0 - keep.mean()
+        changed += (ref[..., :3] != plain[t, ..., :3]).mean()
+        if not keep.any():
+            break  # a global decision on the threshold: the recurrent states may diverge from here
+        m16, frac16, _ = u8_stats(got[t][keep][:, :3], emu[keep][:, :3])
+        m32, _, psnr32 = u8_stats(got[t][keep][:, :3], ref[keep][:, :3])
         assert m16 <= 1 and frac16 < 0.08, (t, m16, frac16)
         assert m32 <= 2 and psnr32 >= 45.0, (t, m32, psnr32)
+    rt.close()
+    # the filter must actually change the picture on this sequence, and the exclusion stays small
+    assert changed / len(frames) > 0.05
+    assert excluded / len(frames) < 0.25
 
 
 def test_filter_off_is_bit_identical_to_no_filter(tmp_path):
