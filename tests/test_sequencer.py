@@ -1,0 +1,106 @@
+"""Frame sequencing policy (avisynth_plugin/src/main.cc:75-161): the C++ header,
+its Python twin and an independent brute-force model must agree request by request."""
+
+import os
+import shutil
+import subprocess
+
+import pytest
+
+from joshupscale_b200 import sequencer as js
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SCRIPTS = [
+    list(range(0, 40)),                                    # plain playback after the mirrored warm-up
+    [0, 1, 2, 1, 0, 3],                                    # warm-up outputs are not cached: 1 and 0 restart
+    list(range(0, 40)) + [39, 30, 24, 23, 40, 41],         # ring cache hits, then a miss beyond the ring
+    [100, 101, 90, 150, 149, 166, 167, 200],               # seeks: within reach, out of reach, backwards
+    [5, 25, 21, 22, 60, 44, 61],
+]
+
+
+def _model(requests):
+    """Straight restatement of the plugin's recursion with explicit lists."""
+    nxt, cache, dont = -16, [], 16
+    calls = 0
+    hits = resets = backtracks = 0
+    lines = []
+    for n in requests:
+        processed = []
+        out = None
+        if n < nxt and nxt - n <= len(cache):
+            hits += 1
+            out = cache[len(cache) - (nxt - n)]
+        else:
+            if n < nxt:
+                nxt, cache, dont = n - 16, [], 16
+                resets += 1
+            if n > nxt:
+                if nxt + 16 < n:
+                    nxt, cache, dont = n - 16, [], 16
+                    resets += 1
+                backtracks += 1
+            while nxt <= n:
+                calls += 1
+                out = 1000 * calls + abs(nxt)
+                processed.append(abs(nxt))
+                nxt += 1
+                if dont > 0:
+                    dont -= 1
+                else:
+                    cache.append(out)
+                    cache = cache[-16:]
+        lines.append(f"{n} -> {out} | {' '.join(map(str, processed))} | {hits} {resets} {backtracks} {nxt}"
+                     .replace("|  |", "| |"))
+    return lines
+
+
+def _python(requests):
+    calls = [0]
+    processed = []
+
+    def process(src):
+        calls[0] += 1
+        processed.append(src)
+        return 1000 * calls[0] + src
+
+    seq = js.FrameSequencer(lambda i: i, process)
+    lines = []
+    for n in requests:
+        processed.clear()
+        out = seq.get(n)
+        lines.append(f"{n} -> {out} | {' '.join(map(str, processed))} | "
+                     f"{seq.stats.cache_hits} {seq.stats.resets} {seq.stats.backtracks} {seq.next}"
+                     .replace("|  |", "| |"))
+    return lines
+
+
+@pytest.mark.parametrize("requests", SCRIPTS)
+def test_python_twin_matches_model(requests):
+    assert _python(requests) == _model(requests)
+
+
+def test_first_request_warms_up_over_mirrored_frames():
+    lines = _python([0])
+    # frames -16..-1 are the clip mirrored around 0, then frame 0 itself
+    assert lines[0].split(" | ")[1] == " ".join(str(abs(k)) for k in range(-16, 1))
+
+
+@pytest.fixture(scope="module")
+def trace_binary(tmp_path_factory):
+    cxx = shutil.which("g++")
+    if not cxx:
+        pytest.skip("no g++")
+    out = str(tmp_path_factory.mktemp("seq") / "sequencer_trace")
+    subprocess.run([cxx, "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cxx", "sequencer_trace.cc"), "-o", out], check=True)
+    return out
+
+
+@pytest.mark.parametrize("requests", SCRIPTS)
+def test_cxx_header_matches_model(trace_binary, requests):
+    got = subprocess.run([trace_binary] + [str(n) for n in requests], check=True, capture_output=True,
+                         text=True).stdout.splitlines()
+    want = _model(requests)
+    assert [" ".join(g.split()) for g in got] == [" ".join(w.split()) for w in want]
