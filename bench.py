@@ -304,20 +304,30 @@ def run_ours(args):
         achieved = grp["flops"] / (res_usec * 1e-6) / 1e12
         peak = peaks["tensor_sustained"]
         persistent = len(res) == 1 and layers > 1
+        # the persistent trunk runs as ceil(streams / chunk) launches of `chunk` streams (engine.cc)
+        chunk = int(os.environ.get("JU_TRUNK_SUBBATCH", "2")) if persistent else 0
+        if chunk <= 0 or chunk > streams:
+            chunk = streams
+        trunk_launches = -(-streams // chunk) if persistent else len(res)
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath) and (h, w) == (270, 480):
             tj = json.load(open(tpath))
-            traffic = tj.get(f"batch{streams}_270x480")
+            if persistent:
+                per_layer = tj.get(f"trunk_df_per_layer_{chunk}_streams")
+                traffic = per_layer * layers if per_layer else None
+            else:
+                traffic = tj.get(f"batch{streams}_270x480")
         roofline = {
             "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
             "frac": achieved / peak, "traffic": traffic,
-            "traffic_note": "dram bytes per layer from ncu --set full of the per-layer kernel (profiles/ncu_traffic.json); "
-                            "algorithmic bytes per layer = %d" % int(bytes_per_layer),
-            "kernel": ("trunk_tc_kernel: all ResBlock conv3x3 64->64 layers in one persistent launch"
+            "traffic_note": "dram bytes per launch (all layers, %d stream(s)) from ncu --set full of this kernel inside "
+                            "bench.py (profiles/ncu_traffic.json); algorithmic bytes per launch = %d"
+                            % (chunk if persistent else streams, int(bytes_per_layer * layers / max(trunk_launches, 1))),
+            "kernel": ("trunk_df_tc_kernel: all ResBlock conv3x3 64->64 layers of %d stream(s) in one persistent launch" % chunk
                        if persistent else "conv_tc_kernel<3,1>: ResBlock conv3x3 64->64 (generator/block_*/conv_*)"),
-            "layers_per_step": layers, "kernel_launches_per_step": len(res), "usec_per_layer": mean_usec,
-            "usec_per_launch": res_usec / len(res),
+            "layers_per_step": layers, "kernel_launches_per_step": trunk_launches, "usec_per_layer": mean_usec,
+            "usec_per_launch": res_usec / trunk_launches,
             "flops_per_layer": flops_per_layer, "share_of_step": res_usec / frame_usec,
             "frac_of_burst_peak": achieved / peaks["tensor_burst"],
             "peak_source": f"{peaks['source']} bf16 dense, sustained (burst {peaks['tensor_burst']})",

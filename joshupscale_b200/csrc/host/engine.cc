@@ -520,6 +520,7 @@ void Engine::buildPlan(int parity) {
 		op.layers = nLayers;
 		op.flops = 2.0 * B * H * W * 9.0 * 64 * 64 * nLayers;
 		op.bytes = static_cast<double>(B) * H * W * 64 * 2.0 * (2.0 * nLayers + 0.5 * nLayers);
+		op.kernels = static_cast<int>(launches.size());
 		int *err = m_TcError.as<int>();
 		op.run = [launches, err, dataflow](cudaStream_t st) {
 			for (const TrunkTcLaunch &l : launches) {
@@ -608,6 +609,7 @@ Op Engine::filterOp(const FrameIO *io, __half *preGenNext, const float *bright) 
 	const int B = m_Batch, H = m_Spec.frameH, W = m_Spec.frameW;
 	Op op;
 	op.name = "frame_moving_avg";
+	op.kernels = m_Filter.window == 0 ? 3 : 2;
 	// two passes over out (4 x fp16) and pw (fp16) + u8 image + fp16 state
 	op.bytes = static_cast<double>(B) * (2.0 * (16.0 * H * W * 8 + H * W * 128.0) + 16.0 * H * W * (4 + 8));
 	const __half *outRaw = m_OutRaw.as<__half>();

@@ -44,6 +44,7 @@ struct Op {
 	double bytes = 0;  // algorithmic bytes moved
 	bool tensorBound = false;
 	int layers = 1;  // network layers covered by this launch (the persistent trunk covers many)
+	int kernels = 1;  // kernel launches issued by run()
 };
 
 struct NamedTensor {
@@ -66,7 +67,11 @@ public:
 	int batch() const { return m_Batch; }
 	int device() const { return m_Device; }
 	int convImpl() const { return m_ConvImpl; }
-	std::size_t kernelsPerFrame() const { return m_Plans[0].size(); }
+	std::size_t kernelsPerFrame() const {
+		std::size_t n = 0;
+		for (const Op &op : m_Plans[0]) n += static_cast<std::size_t>(op.kernels);
+		return n;
+	}
 
 	// n <= batch images; streams beyond n are advanced on their last input.
 	void process(int n, const ju_image *inputs, const ju_image *outputs);
