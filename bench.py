@@ -68,13 +68,35 @@ def load_peaks():
 
 
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region: NVML polled every 5 ms from a
+    thread (the recipe's nvidia-smi -lms 200 line yields too few samples for a 0.1 s region);
+    falls back to the nvidia-smi loop when pynvml is unavailable."""
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap,power.draw")
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+               "sw_power_cap": 0x4}  # nvmlClocksEventReason* bit masks
 
     def __init__(self, device: int):
+        self.samples = []  # (sm_mhz, reasons bitmask, power_w)
+        self.max_mhz = None
         self.lines = []
         self.proc = None
+        self.stop_flag = threading.Event()
+        self.nvml = None
+        try:
+            import pynvml  # noqa: PLC0415
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            index = int(visible.split(",")[device]) if visible and visible.split(",")[device].isdigit() else device
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:  # noqa: BLE001 - any NVML problem: use the nvidia-smi loop
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
@@ -84,11 +106,42 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                try:
+                    mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:  # noqa: BLE001 - older binding name
+                    mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                try:
+                    power = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                except Exception:  # noqa: BLE001
+                    power = None
+                self.samples.append((mhz, mask, power))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.005)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            sm = [s[0] for s in self.samples]
+            mask = 0
+            for s in self.samples:
+                mask |= s[1]
+            powers = [s[2] for s in self.samples if s[2] is not None]
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_min_mhz": min(sm) if sm else None,
+                    "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(k for k, bit in self.REASONS.items() if mask & bit),
+                    "power_w_max": max(powers) if powers else None,
+                    "samples": len(sm), "source": "nvml, 5 ms period over both timed regions"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -112,7 +165,7 @@ class ClockSampler:
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi -lms 200"}
 
 
 def dist_env():
