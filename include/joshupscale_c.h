@@ -136,7 +136,8 @@ JU_API int64_t ju_pack_conv_weights(int impl, const float *kernel, const float *
 /* Global integer options: "tc_variant" (tcgen05 conv halo layout, see
  * conv_tc.cu: 0 = 18x10-pixel halo box, 1 = 18x16-pixel cross-check layout),
  * "tc_tma_epilogue" (0/1: shared-memory epilogue with TMA residual load and
- * TMA store), "tc_pdl" (0/1: programmatic dependent launch). */
+ * TMA store), "tc_pdl" (0/1: programmatic dependent launch), "tc_dual" (0/1: two alternating
+ * producer / issuer pipelines in conv_tc where the layer allows it). */
 JU_API int ju_set_option(const char *key, int value);
 
 /* Stand-alone timing of one convolution shape: allocates its own buffers,

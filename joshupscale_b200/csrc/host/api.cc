@@ -371,6 +371,8 @@ int ju_set_option(const char *key, int value) {
 			ju::conv_tc_set_flags(value, -1);
 		} else if (std::strcmp(key, "tc_pdl") == 0) {
 			ju::conv_tc_set_flags(-1, value);
+		} else if (std::strcmp(key, "tc_dual") == 0) {
+			ju::conv_tc_set_dual(value);
 		} else {
 			throw std::invalid_argument(std::string("unknown option ") + key);
 		}

@@ -41,6 +41,7 @@ Engine::Engine(const ModelFile &model, int device, int batch)
 	if (const char *v = std::getenv("JU_TC_VARIANT")) conv_tc_set_variant(std::atoi(v));
 	if (const char *v = std::getenv("JU_TC_TMA_EPILOGUE")) conv_tc_set_flags(std::atoi(v), -1);
 	if (const char *v = std::getenv("JU_TC_PDL")) conv_tc_set_flags(-1, std::atoi(v));
+	if (const char *v = std::getenv("JU_TC_DUAL")) conv_tc_set_dual(std::atoi(v));
 	m_UseGraph = envInt("JU_NO_GRAPH", 0) == 0;
 	m_Conv2Cta = envInt("JU_CONV_2CTA", 0) != 0;
 	JU_CUDA(cudaStreamCreateWithFlags(&m_Stream, cudaStreamNonBlocking));

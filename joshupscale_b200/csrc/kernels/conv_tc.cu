@@ -41,8 +41,10 @@ namespace {
 
 constexpr int kTileH = 16;  // pixel rows per M tile (= UMMA core-matrix groups)
 constexpr int kTileW = 8;   // pixel columns per M tile (= rows per core-matrix group)
-constexpr int kThreads = 192;       // 2 control warps + 4 epilogue warps
-constexpr int kThreadsWide = 320;   // 2 control warps + 8 epilogue warps (fp16 N=64 epilogue)
+// warps: 0 TMA producer, 1 MMA issuer, then the epilogue warps, then a second producer and a
+// second issuer that are only active in `dual` mode (two independent tile pipelines)
+constexpr int kThreads = 256;       // 4 epilogue warps
+constexpr int kThreadsWide = 384;   // 8 epilogue warps (fp16 N=64 epilogue)
 constexpr int kMaxStages = 8;
 constexpr uint32_t kSmemLimit = 227 * 1024;
 
@@ -61,6 +63,7 @@ struct TcParams {
 	int tma_epi;  // shared-memory epilogue mode: 0 direct, 1 fp16 N=64, 2 fp16 N=32, 3 fp32 N=32
 	int pool;     // fuse MaxPool2D(2) into the epilogue (tma_epi 1/2, no residual)
 	int pdl;      // launched with programmatic stream serialization
+	int dual;     // even / odd tiles run through two independent producer + issuer pipelines
 	uint32_t a_box_bytes, a_region_bytes, stage_bytes, b_slice_bytes;
 	const float *bias;
 	const __half *residual;
@@ -159,10 +162,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 	// kernel in the stream; activations are only touched after the wait.
 	if (p.pdl) grid_launch_dependents();
 
-	if (warp == 0) {
+	constexpr int kEpiWarps = EPI == 1 ? 8 : 4;
+	// Dual mode (kb == 1, resident weights, no residual, even stage count): tiles alternate
+	// between two producer / issuer pairs.  Stage s = tile % stages and TMEM stage = tile & 1, so
+	// each pair owns a disjoint half of the halo ring and one accumulator: two independent
+	// single-producer / single-consumer pipelines.  One issuer's barrier round trips (~300 cycles
+	// each through the shared-memory pipe the operand fetch saturates) then overlap the other
+	// issuer's MMAs instead of draining the tensor pipe between tiles.
+	const bool second = warp >= 2 + kEpiWarps;
+	const int pipe = second ? 1 : 0;
+	if (warp == 0 || (p.dual && warp == 2 + kEpiWarps)) {
 		// ===================== TMA producer =====================
 		if (lane == 0) {
-			if (p.b_resident) {
+			if (p.b_resident && !second) {
 				mbar_arrive_expect_tx(w_bar, resb_bytes);
 				for (int s = 0; s < taps * p.kb; ++s) {
 					// slice s = tap * kb + kbi ; rows [s*cout, s*cout + nt)
@@ -182,10 +194,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 				tma_load_4d(epi_res_base + rb * kEpiTile, &map_r, rfull_bar(rb), t.n0, t.x0, t.y0, t.b);
 			};
 			const bool with_res = p.tma_epi && p.residual;
-			int it = 0, tcount = 0, prev_tile = -1;
+			int tcount = 0, prev_tile = -1;
 			for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+				if (p.dual && (tcount & 1) != pipe) continue;
 				const TileCoord t = decode_tile(p, tile);
-				for (int kbi = 0; kbi < p.kb; ++kbi, ++it) {
+				for (int kbi = 0; kbi < p.kb; ++kbi) {
+					const int it = tcount * p.kb + kbi;
 					const int s = it % p.stages;
 					const uint32_t ph = (it / p.stages) & 1;
 					mbar_wait(empty_bar(s), ph ^ 1u, p.error_flag, 1);
@@ -205,7 +219,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 			}
 			if (with_res && prev_tile >= 0) load_residual(tcount - 1, prev_tile);
 		}
-	} else if (warp == 1) {
+	} else if (warp == 1 || (p.dual && warp == 3 + kEpiWarps)) {
 		// ===================== MMA issuer =====================
 		// One thread issues every tcgen05.mma of the CTA, so its instruction
 		// stream is the critical path: descriptors are split into a constant high
@@ -223,14 +237,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 			if (p.b_resident) {
 				mbar_wait(w_bar, 0, p.error_flag, 2);
 			}
-			int it = 0, tcount = 0;
+			int tcount = 0;
 			for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+				if (p.dual && (tcount & 1) != pipe) continue;
 				const int as = tcount & 1;
 				const uint32_t aph = (tcount >> 1) & 1;
 				mbar_wait(tempty_bar(as), aph ^ 1u, p.error_flag, 3);
 				tcgen05_fence_after();
 				const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.nt);
-				for (int kbi = 0; kbi < p.kb; ++kbi, ++it) {
+				for (int kbi = 0; kbi < p.kb; ++kbi) {
+					const int it = tcount * p.kb + kbi;
 					const int s = it % p.stages;
 					const uint32_t ph = (it / p.stages) & 1;
 					mbar_wait(full_bar(s), ph, p.error_flag, 4);
@@ -260,8 +276,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 				}
 			}
 		}
-	} else {
-		// ===================== epilogue (warps 2..5) =====================
+	} else if (warp >= 2 && warp < 2 + kEpiWarps) {
+		// ===================== epilogue (warps 2..5 or 2..9) =====================
 		const int q = warp & 3;  // TMEM lane quarter this warp may access
 		const int row = q * 32 + lane;
 		const int cpp = p.shuffle2 ? p.cout / 4 : p.cout;  // channels per output pixel
@@ -533,6 +549,7 @@ EncodeTiledFn encodeTiled() {
 int g_TcVariant = 0;
 int g_TcTmaEpi = 1;
 int g_TcPdl = 1;
+int g_TcDual = 1;
 
 }  // namespace
 
@@ -541,6 +558,7 @@ void conv_tc_set_flags(int tma_epilogue, int pdl) {
 	if (tma_epilogue >= 0) g_TcTmaEpi = tma_epilogue;
 	if (pdl >= 0) g_TcPdl = pdl;
 }
+void conv_tc_set_dual(int on) { g_TcDual = on; }
 int conv_tc_get_variant() { return g_TcVariant; }
 
 bool conv_tc_supported(const ConvArgs &a) {
@@ -646,6 +664,12 @@ cudaError_t conv_tc_prepare(const ConvArgs &a, int variant, ConvTcLaunch *out) {
 	if (fixed + 2 * p.stage_bytes > kSmemLimit) return cudaErrorInvalidValue;
 	int stages = static_cast<int>((kSmemLimit - fixed) / p.stage_bytes);
 	if (stages > kMaxStages) stages = kMaxStages;
+	// dual pipelines need an even stage count (disjoint halves of the ring, see the kernel)
+	p.dual = 0;
+	if (g_TcDual && p.kb == 1 && p.b_resident && !a.residual && stages >= 4) {
+		p.dual = 1;
+		stages &= ~1;
+	}
 	p.stages = stages;
 	p.bias = a.bias;
 	p.residual = a.residual;

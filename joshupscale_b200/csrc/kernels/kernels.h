@@ -87,6 +87,7 @@ void conv_tc_set_variant(int v);
 // -1 keeps the current value.  tma_epilogue: shared-memory epilogue with TMA
 // residual load + TMA store; pdl: programmatic dependent launch.
 void conv_tc_set_flags(int tma_epilogue, int pdl);
+void conv_tc_set_dual(int on);  // two alternating producer / issuer pipelines where the layer allows (default on)
 int conv_tc_get_variant();
 
 // ---- fused generator tail (tail_tc.cu): conv_trans_1 GEMM + conv_trans_2 +

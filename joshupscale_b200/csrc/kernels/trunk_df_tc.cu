@@ -487,6 +487,12 @@ cudaError_t trunk_df_tc_prepare(const TrunkArgs &a, TrunkTcLaunch *out) {
 	p.cstride = a.cstride;
 	int stages = static_cast<int>((kSmemLimit - kFixed) / kARegion);
 	if (stages > kMaxStages) stages = kMaxStages;
+	// The two producer / issuer pairs take tiles alternately.  With an EVEN stage count each pair
+	// owns a disjoint set of halo stages, i.e. two independent single-producer / single-consumer
+	// rings; an odd count would let one pair wait on a barrier whose previous phase belongs to the
+	// other pair and may not even have started (mbarrier parity waits alias two phases apart).
+	stages &= ~1;
+	static_assert(kAccStages % 2 == 0, "TMEM stages must split evenly between the two issuers");
 	if (stages < 2) return cudaErrorInvalidValue;
 	p.stages = stages;
 	TrunkMaps maps;
