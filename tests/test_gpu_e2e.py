@@ -302,3 +302,38 @@ def test_sequencer_drives_the_runtime_like_the_avisynth_filter(tmp_path):
         for k in range(14, 31):
             want = manual.process(clip[k])
         np.testing.assert_array_equal(far, want)
+
+
+def test_pinned_host_output_is_written_in_place_and_matches_staged_copy(tmp_path):
+    """Page-locked output buffers are stored to directly by the last kernel (no trailing D2H copy);
+    pageable ones go through the staged copy.  Both must give the same bytes, for top-down and
+    bottom-up images, and bytes outside the image rows must stay untouched."""
+    import ctypes as C
+    cfg, _, path = make_model(tmp_path, "small")
+    h, w = cfg.frame_height, cfg.frame_width
+    oh, ow = 4 * h, 4 * w
+    frames = synthetic.frames(h, w, 3)
+    lib = jrt.load_library()
+    pitch = ow * 4 + 64  # padded rows
+    p_out = C.c_void_p()
+    jrt._check(lib.ju_host_alloc(C.byref(p_out), pitch * oh))
+    try:
+        pinned = np.ctypeslib.as_array(C.cast(p_out, C.POINTER(C.c_uint8)), shape=(oh, pitch))
+        with jrt.Runtime(path, 0, 1) as a, jrt.Runtime(path, 0, 1) as b:
+            for t, f in enumerate(frames):
+                want = a.process(f)  # pageable numpy output: staged copy
+                pinned[...] = 0xAB
+                src = np.ascontiguousarray(f)
+                i = jrt.JuImage(src.ctypes.data, jrt.LOC_CPU, w * 4, w, h)
+                if t % 2 == 0:
+                    o = jrt.JuImage(p_out.value, jrt.LOC_CPU, pitch, ow, oh)
+                    b.process_images([i], [o])
+                    got = pinned[:, :ow * 4].reshape(oh, ow, 4)
+                else:  # bottom-up: pointer to the last memory row, negative stride
+                    o = jrt.JuImage(p_out.value + (oh - 1) * pitch, jrt.LOC_CPU, -pitch, ow, oh)
+                    b.process_images([i], [o])
+                    got = pinned[::-1, :ow * 4].reshape(oh, ow, 4)
+                np.testing.assert_array_equal(got, want)
+                assert (pinned[:, ow * 4:] == 0xAB).all()
+    finally:
+        jrt._check(lib.ju_host_free(p_out))
