@@ -43,7 +43,6 @@ Engine::Engine(const ModelFile &model, int device, int batch)
 	if (const char *v = std::getenv("JU_TC_PDL")) conv_tc_set_flags(-1, std::atoi(v));
 	if (const char *v = std::getenv("JU_TC_DUAL")) conv_tc_set_dual(std::atoi(v));
 	m_UseGraph = envInt("JU_NO_GRAPH", 0) == 0;
-	m_ZeroCopyOut = envInt("JU_ZEROCOPY_OUT", 1) != 0;
 	m_Conv2Cta = envInt("JU_CONV_2CTA", 0) != 0;
 	JU_CUDA(cudaStreamCreateWithFlags(&m_Stream, cudaStreamNonBlocking));
 	try {
@@ -692,19 +691,6 @@ void Engine::bindImages(int n, const ju_image *inputs, const ju_image *outputs) 
 		}
 		if (out.location == JU_LOC_CPU) {
 			if (absStride(out.stride) < outRow) throw std::invalid_argument("output stride smaller than a row");
-			// Page-locked host memory is addressable from the device (UVA): the last kernel then
-			// stores the image straight into the caller's buffer while it computes, and the frame
-			// does not end with a separate 8 MB device-to-host copy behind the kernel.  With the
-			// output filter the image is written twice, so that case keeps the staged copy.
-			void *mapped = m_ZeroCopyOut && !m_FilterOn && out.stride % 16 == 0 &&
-			                       reinterpret_cast<std::uintptr_t>(out.ptr) % 16 == 0
-			                   ? mappedHostPointer(out.ptr)
-			                   : nullptr;
-			if (mapped) {
-				f.out = static_cast<std::uint8_t *>(mapped);
-				f.out_stride = out.stride;
-				continue;
-			}
 			m_OutputNeedsCopy[s] = true;
 			if (out.stride >= 0) {
 				f.out = outStage;
@@ -721,18 +707,6 @@ void Engine::bindImages(int n, const ju_image *inputs, const ju_image *outputs) 
 		}
 	}
 	JU_CUDA(cudaMemcpyAsync(m_IoDev.get(), io, sizeof(FrameIO) * m_Batch, cudaMemcpyHostToDevice, m_Stream));
-}
-
-// Device-side alias of a page-locked host pointer (cudaHostAlloc / cudaHostRegister), nullptr for
-// pageable memory.
-void *Engine::mappedHostPointer(void *host) {
-	cudaPointerAttributes attr{};
-	if (cudaPointerGetAttributes(&attr, host) != cudaSuccess) {
-		cudaGetLastError();
-		return nullptr;
-	}
-	if (attr.type != cudaMemoryTypeHost || !attr.devicePointer) return nullptr;
-	return attr.devicePointer;
 }
 
 void Engine::process(int n, const ju_image *inputs, const ju_image *outputs) {

@@ -93,7 +93,6 @@ private:
 	void registerTensor(const std::string &name, void *p0, void *p1, int dtype,
 	    std::vector<std::uint64_t> dims, std::size_t bytes, bool writable);
 	void bindImages(int n, const ju_image *inputs, const ju_image *outputs);
-	static void *mappedHostPointer(void *host);
 
 	ModelSpec m_Spec;
 	int m_Device = 0;
@@ -101,7 +100,6 @@ private:
 	int m_SmCount = 1;
 	int m_ConvImpl = 0;
 	bool m_UseGraph = true;
-	bool m_ZeroCopyOut = true;
 	bool m_Conv2Cta = false;
 	int m_Parity = 0;
 	cudaStream_t m_Stream = nullptr;

@@ -304,10 +304,11 @@ def test_sequencer_drives_the_runtime_like_the_avisynth_filter(tmp_path):
         np.testing.assert_array_equal(far, want)
 
 
-def test_pinned_host_output_is_written_in_place_and_matches_staged_copy(tmp_path):
-    """Page-locked output buffers are stored to directly by the last kernel (no trailing D2H copy);
-    pageable ones go through the staged copy.  Both must give the same bytes, for top-down and
-    bottom-up images, and bytes outside the image rows must stay untouched."""
+def test_pinned_and_pageable_host_outputs_agree(tmp_path):
+    """Page-locked and pageable output buffers must receive the same bytes, for top-down and
+    bottom-up images with padded rows, and bytes outside the image rows must stay untouched.
+    (Storing the image straight into page-locked memory from the last kernel was measured 3.4x
+    slower end to end than the staged copy - 16-byte PCIe writes - and is not done.)"""
     import ctypes as C
     cfg, _, path = make_model(tmp_path, "small")
     h, w = cfg.frame_height, cfg.frame_width
@@ -321,7 +322,7 @@ def test_pinned_host_output_is_written_in_place_and_matches_staged_copy(tmp_path
         pinned = np.ctypeslib.as_array(C.cast(p_out, C.POINTER(C.c_uint8)), shape=(oh, pitch))
         with jrt.Runtime(path, 0, 1) as a, jrt.Runtime(path, 0, 1) as b:
             for t, f in enumerate(frames):
-                want = a.process(f)  # pageable numpy output: staged copy
+                want = a.process(f)  # pageable numpy output
                 pinned[...] = 0xAB
                 src = np.ascontiguousarray(f)
                 i = jrt.JuImage(src.ctypes.data, jrt.LOC_CPU, w * 4, w, h)
