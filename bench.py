@@ -358,7 +358,9 @@ def run_ours(args):
         peak = peaks["tensor_sustained"]
         persistent = len(res) == 1 and layers > 1
         # the persistent trunk runs as ceil(streams / chunk) launches of `chunk` streams (engine.cc)
-        chunk = int(os.environ.get("JU_TRUNK_SUBBATCH", "2")) if persistent else 0
+        chunk = int(os.environ.get("JU_TRUNK_SUBBATCH", "-1")) if persistent else 0
+        if chunk < 0:  # engine default: streams whose three trunk tensors fit 85 % of the 126 MB L2
+            chunk = max(1, int(0.85 * 126 * 2 ** 20 / (3 * h * w * 64 * 2)))
         if chunk <= 0 or chunk > streams:
             chunk = streams
         trunk_launches = -(-streams // chunk) if persistent else len(res)

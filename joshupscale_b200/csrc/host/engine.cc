@@ -494,15 +494,23 @@ void Engine::buildPlan(int parity) {
 		ta.slope = first->slope;
 		// JU_TRUNK_SYNC: 1 = per-wave dataflow counters (trunk_df_tc.cu), 0 = grid barrier per layer
 		// (trunk_tc.cu), -1 (default) = dataflow.
-		// JU_TRUNK_SUBBATCH (default 2): with the dataflow trunk a large batch runs as consecutive
-		// launches of this many streams, each through ALL layers: three trunk tensors of 2 PSP streams
-		// (100 MB) stay resident in the 126 MB L2, while one launch over 16 streams streams ~800 MB per
-		// layer through HBM.  0 = one launch for the whole batch.
+		// JU_TRUNK_SUBBATCH: with the dataflow trunk a large batch runs as consecutive launches of this
+		// many streams, each through ALL layers, so that the three trunk tensors of one launch stay
+		// resident in L2 (2 PSP streams = 100 MB of the 126 MB; one launch over 16 streams would
+		// stream ~800 MB per layer through HBM).  Default (-1): as many streams as fit 85 % of the
+		// L2; 0 = one launch for the whole batch.
 		const int syncMode = envInt("JU_TRUNK_SYNC", -1);
 		const bool dataflow = syncMode != 0;
-		int chunk = dataflow ? envInt("JU_TRUNK_SUBBATCH", 2) : 0;
-		if (chunk <= 0 || chunk > B) chunk = B;
 		const std::size_t perStream = static_cast<std::size_t>(H) * W * gs;
+		int chunk = dataflow ? envInt("JU_TRUNK_SUBBATCH", -1) : 0;
+		if (chunk < 0) {
+			int l2 = 0;
+			cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, m_Device);
+			const double budget = 0.85 * static_cast<double>(l2);
+			chunk = static_cast<int>(budget / (3.0 * perStream * sizeof(__half)));
+			if (chunk < 1) chunk = 1;
+		}
+		if (chunk <= 0 || chunk > B) chunk = B;
 		const std::size_t tilesPerStream = static_cast<std::size_t>((H + 15) / 16) * ((W + 7) / 8);
 		std::vector<TrunkTcLaunch> launches;
 		for (int b0 = 0; b0 < B; b0 += chunk) {
