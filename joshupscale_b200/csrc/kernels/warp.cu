@@ -20,6 +20,7 @@ namespace ju {
 namespace {
 
 constexpr int kLrTile = 16;  // LR pixels per block (one LR row segment) -> 64x4 HR pixels
+constexpr int kTilePitch = 72;  // halfs per staged pixel row (64 + 8 padding)
 
 __device__ __forceinline__ float preprocess_px(unsigned int v) {
 	return __fsub_rn(__fdiv_rn(static_cast<float>(v), 255.0f), 0.5f);
@@ -31,8 +32,11 @@ __global__ void __launch_bounds__(256) warp_s2d_kernel(const __half *__restrict_
     float *__restrict__ taps, const float *__restrict__ brightness, int h, int w, int ph, int pw,
     int cstride) {
 	// staging tile: kLrTile LR pixels x 64 channels fp16, written out as full
-	// 128-byte pixel rows (coalesced) after the gather
-	__shared__ __align__(16) __half tile[kLrTile][64];
+	// 128-byte pixel rows (coalesced) after the gather.  Rows are padded to 144 bytes: a warp
+	// spans 8 LR pixels (one HR row of 32 pixels keeps the gathers coalesced), and with a
+	// 128-byte pitch its 2-byte stores to 8 rows hit the same banks (8-way conflict); the
+	// 16-byte skew spreads them.
+	__shared__ __align__(16) __half tile[kLrTile][kTilePitch];
 
 	const int b = blockIdx.z;
 	const int ly = blockIdx.y;
