@@ -193,6 +193,10 @@ JU_API int ju_l2_flush(void);
  * synchronises and returns the elapsed device time in microseconds. */
 JU_API int ju_timer_begin(void);
 JU_API int ju_timer_end(double *usec);
+/* Self-check of the kernels' u8 -> float conversion (PreprocessLayer, keras_layers.py:195-208):
+ * fills two HOST arrays of 256 floats with x/255 - 0.5 as the kernels compute it (division-free)
+ * and as an IEEE fp32 division computes it; they must be bit-identical. */
+JU_API int ju_u8_conversion_table(float *fast256, float *ieee256);
 
 #ifdef __cplusplus
 }

@@ -575,6 +575,18 @@ int ju_l2_flush(void) {
 	});
 }
 
+int ju_u8_conversion_table(float *fast256, float *ieee256) {
+	return guarded([&] {
+		requireDevice();
+		if (!fast256 || !ieee256) throw std::invalid_argument("null table pointer");
+		ju::DeviceBuffer buf(2 * 256 * sizeof(float));
+		float *d = buf.as<float>();
+		ju::checkCuda(ju::launch_u8_table(d, d + 256, nullptr), "launch_u8_table");
+		JU_CUDA(cudaMemcpy(fast256, d, 256 * sizeof(float), cudaMemcpyDeviceToHost));
+		JU_CUDA(cudaMemcpy(ieee256, d + 256, 256 * sizeof(float), cudaMemcpyDeviceToHost));
+	});
+}
+
 int ju_timer_begin(void) {
 	return guarded([&] {
 		requireDevice();

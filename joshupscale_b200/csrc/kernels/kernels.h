@@ -50,6 +50,10 @@ cudaError_t launch_preprocess(const FrameIO *io, const __half *flow_prev, __half
 // out[b] = mean over (h, w, c) of cur * BGR_LUMA * 3, deterministic summation order
 cudaError_t launch_brightness(const FrameIO *io, float *out, int batch, int h, int w, cudaStream_t s);
 
+// u8 -> float conversion table: the division-free kernel formulation and the IEEE-division
+// reference for all 256 byte values (device pointers to 256 floats each)
+cudaError_t launch_u8_table(float *fast256, float *ieee256, cudaStream_t s);
+
 cudaError_t launch_conv_simt(const ConvArgs &a, cudaStream_t s);
 // bytes of the SIMT weight layout [tap][cin_padded][cout] fp16
 size_t conv_simt_weight_bytes(int ksize, int cin_padded, int cout);

@@ -7,6 +7,7 @@
 // / Add / ClipLayer / PostprocessLayer (scripts/training/models.py:573-593,
 // 768-789; keras_layers.py:208, 227-230).
 #include "kernels.h"
+#include "pixel_common.cuh"
 
 namespace ju {
 
@@ -14,10 +15,6 @@ namespace {
 
 // float32(u8) / 255 - 0.5 with the exact rounding of the fp32 reference
 // (keras_layers.py:208); no FMA contraction.
-__device__ __forceinline__ float preprocess_px(unsigned int v) {
-	return __fsub_rn(__fdiv_rn(static_cast<float>(v), 255.0f), 0.5f);
-}
-
 // ---------------------------------------------------------------------
 // preprocess: one thread per padded LR pixel.
 //   next[0:3]   = cur (0 inside the zero padding)   models.py:780-789
@@ -203,7 +200,18 @@ __global__ void __launch_bounds__(1024) brightness_kernel(const FrameIO *__restr
 	if (threadIdx.x == 0) out[blockIdx.x] = part[0] / static_cast<float>(3 * n);
 }
 
+// both formulations of the u8 -> float conversion for every byte value (self-check entry)
+__global__ void u8_table_kernel(float *fast, float *ieee) {
+	fast[threadIdx.x] = preprocess_px(threadIdx.x);
+	ieee[threadIdx.x] = preprocess_px_ieee(threadIdx.x);
+}
+
 }  // namespace
+
+cudaError_t launch_u8_table(float *fast256, float *ieee256, cudaStream_t s) {
+	u8_table_kernel<<<1, 256, 0, s>>>(fast256, ieee256);
+	return cudaGetLastError();
+}
 
 cudaError_t launch_brightness(const FrameIO *io, float *out, int batch, int h, int w, cudaStream_t s) {
 	brightness_kernel<<<batch, 1024, 0, s>>>(io, out, h, w);

@@ -19,6 +19,7 @@
 #include <cstring>
 
 #include "kernels.h"
+#include "pixel_common.cuh"
 #include "tc_common.cuh"
 
 namespace ju {
@@ -49,10 +50,6 @@ struct TailParams {
 	const float *brightness;  // optional [batch]
 	int *error_flag;
 };
-
-__device__ __forceinline__ float preprocess_px(unsigned int v) {
-	return __fsub_rn(__fdiv_rn(static_cast<float>(v), 255.0f), 0.5f);
-}
 
 // tanh(x) = 1 - 2 / (exp(2x) + 1) with ex2.approx / fast division: absolute error
 // below 1e-6 (vs 1 - 2 ulp of tanhf), ~6 instructions instead of ~40.

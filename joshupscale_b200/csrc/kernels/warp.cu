@@ -14,6 +14,7 @@
 // oracle given the same flow; the three lerps use the reference's order
 // top = ax*(TR-TL)+TL ; bot = ax*(BR-BL)+BL ; out = ay*(bot-top)+top.
 #include "kernels.h"
+#include "pixel_common.cuh"
 
 namespace ju {
 
@@ -21,10 +22,6 @@ namespace {
 
 constexpr int kLrTile = 16;  // LR pixels per block (one LR row segment) -> 64x4 HR pixels
 constexpr int kTilePitch = 72;  // halfs per staged pixel row (64 + 8 padding)
-
-__device__ __forceinline__ float preprocess_px(unsigned int v) {
-	return __fsub_rn(__fdiv_rn(static_cast<float>(v), 255.0f), 0.5f);
-}
 
 template <bool kTaps, bool kBright>
 __global__ void __launch_bounds__(256) warp_s2d_kernel(const __half *__restrict__ pre_gen,

@@ -89,6 +89,7 @@ SYMBOLS = {
     "ju_host_free": (_I, [_VP]),
     "ju_l2_flush": (_I, []),
     "ju_timer_begin": (_I, []),
+    "ju_u8_conversion_table": (_I, [C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "ju_timer_end": (_I, [C.POINTER(C.c_double)]),
 }
 

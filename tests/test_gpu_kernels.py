@@ -7,6 +7,7 @@ import pytest
 import torch
 
 from joshupscale_b200 import kernels as jk
+from joshupscale_b200 import runtime as jrt
 from oracle import reference_graph as og
 from tests.gpu_util import r16, require_gpu
 
@@ -153,3 +154,17 @@ def test_final_epilogue(h, w):
     assert d.max() <= 1 and (d > 0).mean() < 2e-3
     np.testing.assert_array_equal(state[..., :3].view(np.uint16), raw.astype(np.float16).view(np.uint16))
     assert not state[..., 3].any()
+
+
+def test_u8_conversion_matches_ieee_division_for_all_bytes():
+    """The kernels convert pixels with a division-free sequence (pixel_common.cuh); it must equal
+    the IEEE fp32 division of the reference formula for every byte value, bit for bit."""
+    import ctypes as C
+    lib = jrt.load_library()
+    fast = (C.c_float * 256)()
+    ieee = (C.c_float * 256)()
+    jrt._check(lib.ju_u8_conversion_table(fast, ieee))
+    fast, ieee = np.frombuffer(fast, np.float32), np.frombuffer(ieee, np.float32)
+    want = np.arange(256, dtype=np.float32) / np.float32(255) - np.float32(0.5)
+    np.testing.assert_array_equal(ieee.view(np.uint32), want.view(np.uint32))
+    np.testing.assert_array_equal(fast.view(np.uint32), want.view(np.uint32))
