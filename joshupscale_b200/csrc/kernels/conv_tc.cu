@@ -44,7 +44,7 @@ constexpr int kTileW = 8;   // pixel columns per M tile (= rows per core-matrix 
 // warps: 0 TMA producer, 1 MMA issuer, then the epilogue warps, then a second producer and a
 // second issuer that are only active in `dual` mode (two independent tile pipelines)
 constexpr int kThreads = 256;       // 4 epilogue warps
-constexpr int kThreadsWide = 384;   // 8 epilogue warps (fp16 N=64 epilogue)
+constexpr int kThreadsWide = 384;   // 8 epilogue warps (every shared-memory epilogue mode)
 constexpr int kMaxStages = 8;
 constexpr uint32_t kSmemLimit = 227 * 1024;
 
@@ -96,7 +96,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams &p, int idx) {
 }
 
 template <int KS, int EPI>
-__global__ void __launch_bounds__(EPI == 1 ? kThreadsWide : kThreads, 1)
+__global__ void __launch_bounds__(EPI != 0 ? kThreadsWide : kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
     const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_r,
     const TcParams p) {
@@ -162,7 +162,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 	// kernel in the stream; activations are only touched after the wait.
 	if (p.pdl) grid_launch_dependents();
 
-	constexpr int kEpiWarps = EPI == 1 ? 8 : 4;
+	constexpr int kEpiWarps = EPI != 0 ? 8 : 4;
 	// Dual mode (kb == 1, resident weights, no residual, even stage count): tiles alternate
 	// between two producer / issuer pairs.  Stage s = tile % stages and TMEM stage = tile & 1, so
 	// each pair owns a disjoint half of the halo ring and one accumulator: two independent
@@ -281,14 +281,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 		const int q = warp & 3;  // TMEM lane quarter this warp may access
 		const int row = q * 32 + lane;
 		const int cpp = p.shuffle2 ? p.cout / 4 : p.cout;  // channels per output pixel
-		const int etid = threadIdx.x - 64;  // index within the epilogue warps
+		// N = 64 (EPI 1): the two warp quartets split the channels of every tile.  N = 32 (EPI 2, 3):
+		// they form two independent groups that take even / odd tiles, each with its own TMEM
+		// stage, staging tile, named barrier and bulk-store group - two tiles drain at once.
+		constexpr bool kGrouped = EPI == 2 || EPI == 3;
+		const int group = kGrouped ? ((warp - 2) >> 2) : 0;
+		const int etid = threadIdx.x - 64 - group * 128;  // index within this warp's epilogue group
 		const int half = EPI == 1 ? ((warp - 2) >> 2) : 0;  // 32-channel half handled by this warp
+		bool first_tile = true;
+		auto group_barrier = [&]() {
+			if constexpr (EPI == 1) {
+				epilogue_barrier<256>();
+			} else {
+				asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
+			}
+		};
 		uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic pointer to the aligned base
 		float bias_reg[32];
 		if (p.pdl) grid_dependency_wait();
 		int tcount = 0;
 		for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
 			const TileCoord t = decode_tile(p, tile);
+			if (kGrouped && (tcount & 1) != group) continue;
 			const int as = tcount & 1;
 			const uint32_t aph = (tcount >> 1) & 1;
 			if constexpr (EPI != 0) {
@@ -303,13 +317,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 				// TMEM is released before the math.
 				constexpr int kTC = EPI == 3 ? 8 : 4;  // 16-byte chunks produced per thread
 				const int coff = EPI == 1 ? half * 4 : 0;  // first chunk of this thread's channels
-				if (tcount == 0 || p.n_tiles > 1) {
+				if (first_tile || p.n_tiles > 1) {
 #pragma unroll
 					for (int c = 0; c < 32; ++c) bias_reg[c] = p.bias ? __ldg(p.bias + t.n0 + half * 32 + c) : 0.f;
+					first_tile = false;
 				}
 				if (etid == 0 && tcount >= 2) {
-					// the bulk store that read staging[as] two tiles ago must have drained
-					asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+					// the bulk store that read staging[as] two tiles ago must have drained (a grouped
+					// leader only has its own group's stores outstanding: that one is its latest)
+					if (kGrouped) {
+						asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+					} else {
+						asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+					}
 				}
 				const uint32_t sw = EPI == 2 ? static_cast<uint32_t>((row >> 1) & 3) : static_cast<uint32_t>(row & 7);
 				uint4 res[4];
@@ -335,7 +355,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 					mbar_arrive(tempty_bar(as));
 					if (EPI != 3 && p.residual) mbar_arrive(rempty_bar(as));
 				}
-				epilogue_barrier<EPI == 1 ? 256 : 128>();  // staging[as] free (wait_group.read above)
+				group_barrier();  // staging[as] free (wait_group.read above)
 				float v[32];
 #pragma unroll
 				for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(acc[c]) + bias_reg[c];
@@ -411,7 +431,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 				}
 				// make the generic-proxy smem writes visible to the TMA (async proxy)
 				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-				epilogue_barrier<EPI == 1 ? 256 : 128>();
+				group_barrier();
 				if (etid == 0) {
 					// out-of-range rows/columns of ragged tiles are clipped by the TMA store
 					if (p.pool) {
@@ -514,7 +534,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 		}
 	}
 
-	if (EPI != 0 && threadIdx.x == 64) {
+	if (EPI != 0 && (threadIdx.x == 64 || ((EPI == 2 || EPI == 3) && threadIdx.x == 64 + 128))) {
 		asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 	}
 	tcgen05_fence_before();
@@ -776,7 +796,7 @@ cudaError_t conv_tc_launch(const ConvTcLaunch &l, int *error_flag, cudaStream_t 
 	p.error_flag = error_flag;
 	cudaLaunchConfig_t cfg{};
 	cfg.gridDim = dim3(l.grid);
-	cfg.blockDim = dim3(p.tma_epi == 1 ? kThreadsWide : kThreads);
+	cfg.blockDim = dim3(p.tma_epi != 0 ? kThreadsWide : kThreads);
 	cfg.dynamicSmemBytes = l.smem_bytes;
 	cfg.stream = s;
 	cudaLaunchAttribute attr[1];
