@@ -293,6 +293,7 @@ Op Engine::convOp(ConvLayer *L, const __half *in, int cinStride, const __half *r
 		ConvArgs t = a;
 		t.weights = L->wTc.get();
 		t.cin = pad64(L->cinReal);
+		t.cin_live = L->cinReal;
 		if (t.cin <= cinStride && m_Conv2Cta && conv_tc2_supported(t)) {
 			// experimental CTA-pair kernel (JU_CONV_2CTA=1): only faster at batch 1, see DESIGN.md 6
 			ConvTcLaunch launch;

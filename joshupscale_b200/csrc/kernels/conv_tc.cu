@@ -64,6 +64,7 @@ struct TcParams {
 	int pool;     // fuse MaxPool2D(2) into the epilogue (tma_epi 1/2, no residual)
 	int pdl;      // launched with programmatic stream serialization
 	int dual;     // even / odd tiles run through two independent producer + issuer pipelines
+	int last_k16; // K steps of 16 channels in the last 64-channel block that are not all zero (1..4)
 	uint32_t a_box_bytes, a_region_bytes, stage_bytes, b_slice_bytes;
 	const float *bias;
 	const __half *residual;
@@ -257,6 +258,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 					                                               : stage + p.a_region_bytes) >> 4);
 					const uint32_t b_tap16 = p.b_resident ? b_slice16 * p.kb : b_slice16;
 					uint32_t first = kbi == 0 ? 0u : 1u;
+					// channels beyond the layer's real Cin are zero in both operands: skip those K steps
+					const int nk16 = kbi == p.kb - 1 ? p.last_k16 : 4;
 					if (elect_one_sync()) {
 #pragma unroll
 					for (int tap = 0; tap < taps; ++tap) {
@@ -264,9 +267,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 						const uint32_t b_tap = b_lo + tap * b_tap16;
 #pragma unroll
 						for (int k16 = 0; k16 < 4; ++k16) {
-							const uint64_t a_desc = (static_cast<uint64_t>(a_hi) << 32) | (a_tap + k16 * 2u);
-							const uint64_t b_desc = (static_cast<uint64_t>(b_hi) << 32) | (b_tap + k16 * 2u);
-							umma_f16(d_tmem, a_desc, b_desc, idesc, (tap | k16) != 0 ? 1u : first);
+							if (k16 < nk16) {
+								const uint64_t a_desc = (static_cast<uint64_t>(a_hi) << 32) | (a_tap + k16 * 2u);
+								const uint64_t b_desc = (static_cast<uint64_t>(b_hi) << 32) | (b_tap + k16 * 2u);
+								umma_f16(d_tmem, a_desc, b_desc, idesc, (tap | k16) != 0 ? 1u : first);
+							}
 						}
 					}
 					umma_commit(empty_bar(s));  // frees the stage when these MMAs have read it
@@ -628,6 +633,11 @@ cudaError_t conv_tc_prepare(const ConvArgs &a, int variant, ConvTcLaunch *out) {
 	p.n_tiles = a.cout / p.nt;
 	p.total_tiles = a.batch * p.tiles_x * p.tiles_y * p.n_tiles;
 	p.kb = a.cin / 64;
+	p.last_k16 = 4;
+	if (a.cin_live > 0 && a.cin_live <= a.cin) {
+		const int live = a.cin_live - 64 * (p.kb - 1);
+		if (live >= 1) p.last_k16 = (live + 15) / 16;  // a fully dead last block is left alone (not expected)
+	}
 	p.ks = a.ksize;
 	p.cout = a.cout;
 	p.cout_stride = a.cout_stride;

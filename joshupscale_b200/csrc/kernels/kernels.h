@@ -32,6 +32,8 @@ struct ConvArgs {
 	int batch, h, w;
 	int cin_stride;          // channel stride of `in` (elements)
 	int cin;                 // channels reduced over (multiple of 16, <= cin_stride)
+	int cin_live;            // 0, or the number of leading channels that can be non-zero (weights and
+	                         // activations beyond are zero): the tcgen05 kernel skips all-zero K steps
 	int cout;                // output channels computed (shuffle2: 4 * per-pixel channels)
 	int cout_stride;         // channel stride of `out` / `residual`
 	int ksize;               // 1 or 3
