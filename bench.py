@@ -341,7 +341,7 @@ def run_ours(args):
         peaks = load_peaks()
         all_ops = rt.profile_ops(10)
         rt.reset_state()
-        ops = [o for o in all_ops if not o["name"].startswith("group:")]
+        ops = [o for o in all_ops if not o["name"].startswith("group:") and not o["name"].startswith("sync:")]
         groups = {o["name"][6:]: o for o in all_ops if o["name"].startswith("group:")}
         # dominant kernel: the generator's ResBlock convs.  Launch duration =
         # CUDA-event time around the back-to-back run of all ResBlock launches
@@ -356,14 +356,14 @@ def run_ours(args):
         mean_usec = res_usec / layers
         achieved = grp["flops"] / (res_usec * 1e-6) / 1e12
         peak = peaks["tensor_sustained"]
-        persistent = len(res) == 1 and layers > 1
+        persistent = any("(persistent)" in o["name"] for o in res)
         # the persistent trunk runs as ceil(streams / chunk) launches of `chunk` streams (engine.cc)
         chunk = int(os.environ.get("JU_TRUNK_SUBBATCH", "-1")) if persistent else 0
         if chunk < 0:  # engine default: streams whose three trunk tensors fit 85 % of the 126 MB L2
             chunk = max(1, int(0.85 * 126 * 2 ** 20 / (3 * h * w * 64 * 2)))
         if chunk <= 0 or chunk > streams:
             chunk = streams
-        trunk_launches = -(-streams // chunk) if persistent else len(res)
+        trunk_launches = len(res)  # one op per sub-batch launch (persistent) or per layer
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath) and (h, w) == (270, 480):
@@ -388,10 +388,14 @@ def run_ours(args):
             "peak_source": f"{peaks['source']} bf16 dense, sustained (burst {peaks['tensor_burst']})",
         }
         hbm_ops = {}
-        for o in ops:
+        for o in ops:  # ops that run once per sub-batch (tail, filter) are summed per name
             if not o["tensor_bound"]:
-                hbm_ops[o["name"]] = {"usec": o["usec"], "gbs": o["bytes"] / (o["usec"] * 1e-6) / 1e9,
-                                      "frac_of_hbm_peak": o["bytes"] / (o["usec"] * 1e-6) / 1e9 / peaks["hbm"]}
+                acc = hbm_ops.setdefault(o["name"], {"usec": 0.0, "bytes": 0.0})
+                acc["usec"] += o["usec"]
+                acc["bytes"] += o["bytes"]
+        for name, acc in hbm_ops.items():
+            gbs = acc["bytes"] / (acc["usec"] * 1e-6) / 1e9 if acc["usec"] > 0 else 0.0
+            hbm_ops[name] = {"usec": acc["usec"], "gbs": gbs, "frac_of_hbm_peak": gbs / peaks["hbm"]}
         flow_usec = groups["flow"]["usec"]
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         with open(os.path.join(ROOT, "gpurun_out", f"ops_{args.workload}.json"), "w") as f:

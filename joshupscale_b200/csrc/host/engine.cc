@@ -45,6 +45,7 @@ Engine::Engine(const ModelFile &model, int device, int batch)
 	m_UseGraph = envInt("JU_NO_GRAPH", 0) == 0;
 	m_Conv2Cta = envInt("JU_CONV_2CTA", 0) != 0;
 	JU_CUDA(cudaStreamCreateWithFlags(&m_Stream, cudaStreamNonBlocking));
+	JU_CUDA(cudaStreamCreateWithFlags(&m_CopyStream, cudaStreamNonBlocking));
 	try {
 		buildLayers(model);
 		if (model.has("meta/frame_moving_avg")) {
@@ -77,6 +78,8 @@ Engine::Engine(const ModelFile &model, int device, int batch)
 	} catch (...) {
 		for (auto &g : m_GraphExec)
 			if (g) cudaGraphExecDestroy(g);
+		for (auto &e : m_ChunkDone) cudaEventDestroy(e);
+		cudaStreamDestroy(m_CopyStream);
 		cudaStreamDestroy(m_Stream);
 		throw;
 	}
@@ -89,8 +92,11 @@ Engine::Engine(const ModelFile &model, int device, int batch)
 Engine::~Engine() {
 	cudaSetDevice(m_Device);
 	cudaStreamSynchronize(m_Stream);
+	cudaStreamSynchronize(m_CopyStream);
 	for (auto &g : m_GraphExec)
 		if (g) cudaGraphExecDestroy(g);
+	for (auto &e : m_ChunkDone) cudaEventDestroy(e);
+	cudaStreamDestroy(m_CopyStream);
 	cudaStreamDestroy(m_Stream);
 }
 
@@ -230,7 +236,8 @@ void Engine::allocate() {
 		filter_geometry(m_Filter, static_cast<int>(H), static_cast<int>(W), &cy, &cx, &pt, &pl);
 		const std::size_t work = std::max<std::size_t>(
 		    filter_partials_per_stream(static_cast<int>(H), static_cast<int>(W)), static_cast<std::size_t>(cy) * cx);
-		m_FilterScratch = DeviceBuffer(B * (1 + work) * sizeof(float));
+		m_FilterScratchPerStream = 1 + work;
+		m_FilterScratch = DeviceBuffer(B * m_FilterScratchPerStream * sizeof(float));
 	}
 
 	registerTensor("flow_in", m_FlowIn[0].get(), m_FlowIn[1].get(), 1,
@@ -513,7 +520,11 @@ void Engine::buildPlan(int parity) {
 		}
 		if (chunk <= 0 || chunk > B) chunk = B;
 		const std::size_t tilesPerStream = static_cast<std::size_t>((H + 15) / 16) * ((W + 7) / 8);
-		std::vector<TrunkTcLaunch> launches;
+		cur = trunk_output_buffer(nLayers) == 0 ? t0 : t2;
+		ConvLayer *ct1c = layer("generator/conv_trans_1");
+		const bool tailPerChunk = chunk < B && m_ConvImpl == 1 && ct1c->wTc.get() && gs % 64 == 0 &&
+		                          s.genFilters == 64 && envInt("JU_FUSED_TAIL", 1) != 0;
+		int *err = m_TcError.as<int>();
 		for (int b0 = 0; b0 < B; b0 += chunk) {
 			TrunkArgs sub = ta;
 			sub.batch = std::min(chunk, B - b0);
@@ -522,26 +533,33 @@ void Engine::buildPlan(int parity) {
 			sub.flags = ta.flags + static_cast<std::size_t>(nLayers) * tilesPerStream * b0;
 			TrunkTcLaunch launch;
 			checkCuda(dataflow ? trunk_df_tc_prepare(sub, &launch) : trunk_tc_prepare(sub, &launch), "trunk_tc_prepare");
-			launches.push_back(launch);
-		}
-		Op op;
-		op.name = "generator/block_*(persistent)";
-		op.tensorBound = true;
-		op.layers = nLayers;
-		op.flops = 2.0 * B * H * W * 9.0 * 64 * 64 * nLayers;
-		op.bytes = static_cast<double>(B) * H * W * 64 * 2.0 * (2.0 * nLayers + 0.5 * nLayers);
-		op.kernels = static_cast<int>(launches.size());
-		int *err = m_TcError.as<int>();
-		op.run = [launches, err, dataflow](cudaStream_t st) {
-			for (const TrunkTcLaunch &l : launches) {
-				cudaError_t e = dataflow ? trunk_df_tc_launch(l, err, st) : trunk_tc_launch(l, err, st);
-				if (e != cudaSuccess) return e;
+			Op op;
+			op.name = "generator/block_*(persistent)";
+			op.tensorBound = true;
+			op.layers = b0 == 0 ? nLayers : 0;  // network layers are counted once, not once per sub-batch
+			op.flops = 2.0 * sub.batch * H * W * 9.0 * 64 * 64 * nLayers;
+			op.bytes = static_cast<double>(sub.batch) * H * W * 64 * 2.0 * (2.0 * nLayers + 0.5 * nLayers);
+			op.run = [launch, err, dataflow](cudaStream_t st) {
+				return dataflow ? trunk_df_tc_launch(launch, err, st) : trunk_tc_launch(launch, err, st);
+			};
+			plan.push_back(std::move(op));
+			++m_TcOps;
+			if (tailPerChunk) {
+				// The sub-batch is finished right away (tail kernel, output filter) and its completion
+				// is published as an event, so that process() can copy these streams' images to the
+				// host while the trunk of the next sub-batch is still running.
+				emitTail(plan, parity, cur, gs, b0, sub.batch);
 			}
-			return cudaSuccess;
-		};
-		plan.push_back(std::move(op));
-		++m_TcOps;
-		cur = trunk_output_buffer(nLayers) == 0 ? t0 : t2;
+		}
+		if (tailPerChunk) {
+			if (parity == 0) {
+				registerTensor("trunk", cur, nullptr, 1,
+				    {static_cast<std::uint64_t>(B), static_cast<std::uint64_t>(H), static_cast<std::uint64_t>(W),
+				        static_cast<std::uint64_t>(gs)},
+				    m_Trunk[0].bytes(), false);
+			}
+			return;
+		}
 	} else {
 		for (int i = 0; i < s.genBlocks; ++i) {
 			std::string p = "generator/block_" + std::to_string(i + 1);
@@ -560,37 +578,7 @@ void Engine::buildPlan(int parity) {
 	const bool fusedTail = m_ConvImpl == 1 && ct1->wTc.get() && gs % 64 == 0 && s.genFilters == 64 &&
 	                       envInt("JU_FUSED_TAIL", 1) != 0;
 	if (fusedTail) {
-		// conv_trans_1 + conv_trans_2 + tanh + upscale + add + clip + pack + state in ONE kernel
-		TailArgs ta{};
-		ta.in = cur;
-		ta.cin_stride = gs;
-		ta.weights1 = ct1->wTc.get();
-		ta.bias1 = ct1->bias.as<float>();
-		ta.w2 = m_W2.as<float>();
-		ta.bias2 = m_B2.as<float>();
-		ta.io = io;
-		ta.pre_gen_next = m_FilterOn ? m_OutRaw.as<__half>() : preGenNext;
-		ta.out_raw = nullptr;
-		ta.brightness = m_FilterOn ? nullptr : bright;
-		ta.batch = B;
-		ta.h = H;
-		ta.w = W;
-		ta.act = ct1->act;
-		ta.slope = ct1->slope;
-		ta.pdl = 1;
-		TailTcLaunch launch;
-		checkCuda(tail_tc_prepare(ta, &launch), "tail_tc_prepare");
-		Op op;
-		op.name = "tail_fused";
-		op.tensorBound = false;
-		// read trunk (64ch fp16) + LR input + write BGRX u8 + fp16 state (3ch), SURVEY 8(d)
-		op.bytes = static_cast<double>(B) * (H * W * 64 * 2.0 + H * W * 4.0 + 16.0 * H * W * (4 + 3 * 2));
-		op.flops = 2.0 * B * H * W * (64.0 * 128 + 4.0 * 32 * 12);
-		int *err = m_TcError.as<int>();
-		op.run = [launch, err](cudaStream_t st) { return tail_tc_launch(launch, err, st); };
-		plan.push_back(std::move(op));
-		++m_TcOps;
-		if (m_FilterOn) plan.push_back(filterOp(io, preGenNext, bright));
+		emitTail(plan, parity, cur, gs, 0, B);
 		return;
 	}
 	plan.push_back(convOp(ct1, cur, gs, nullptr, m_Mid.get(), 32, H, W, false));
@@ -609,22 +597,94 @@ void Engine::buildPlan(int parity) {
 		};
 		plan.push_back(std::move(op));
 	}
-	if (m_FilterOn) plan.push_back(filterOp(io, preGenNext, bright));
+	if (m_FilterOn) plan.push_back(filterOp(io, preGenNext, bright, 0, B));
+	plan.push_back(chunkDoneOp(0, B));
+}
+
+// Fused tail (+ output filter) for streams [b0, b0 + nb), followed by the event that tells
+// process() these streams' images are complete.
+void Engine::emitTail(std::vector<Op> &plan, int parity, const __half *trunkOut, int gs, int b0, int nb) {
+	const int H = m_Spec.frameH, W = m_Spec.frameW;
+	const FrameIO *io = m_IoDev.as<FrameIO>() + b0;
+	const std::size_t hrStream = static_cast<std::size_t>(16) * H * W * 4;  // fp16 elements of one HR state
+	__half *preGenNext = m_PreGen[parity ^ 1].as<__half>() + hrStream * b0;
+	const float *bright = m_Spec.normalizeBrightness ? m_Brightness.as<float>() + b0 : nullptr;
+	ConvLayer *ct1 = m_LayerByName.at("generator/conv_trans_1");
+	// conv_trans_1 + conv_trans_2 + tanh + upscale + add + clip + pack + state in ONE kernel
+	TailArgs ta{};
+	ta.in = trunkOut + static_cast<std::size_t>(H) * W * gs * b0;
+	ta.cin_stride = gs;
+	ta.weights1 = ct1->wTc.get();
+	ta.bias1 = ct1->bias.as<float>();
+	ta.w2 = m_W2.as<float>();
+	ta.bias2 = m_B2.as<float>();
+	ta.io = io;
+	ta.pre_gen_next = m_FilterOn ? m_OutRaw.as<__half>() + hrStream * b0 : preGenNext;
+	ta.out_raw = nullptr;
+	ta.brightness = m_FilterOn ? nullptr : bright;
+	ta.batch = nb;
+	ta.h = H;
+	ta.w = W;
+	ta.act = ct1->act;
+	ta.slope = ct1->slope;
+	ta.pdl = 1;
+	TailTcLaunch launch;
+	checkCuda(tail_tc_prepare(ta, &launch), "tail_tc_prepare");
+	Op op;
+	op.name = "tail_fused";
+	op.tensorBound = false;
+	// read trunk (64ch fp16) + LR input + write BGRX u8 + fp16 state (3ch), SURVEY 8(d)
+	op.bytes = static_cast<double>(nb) * (H * W * 64 * 2.0 + H * W * 4.0 + 16.0 * H * W * (4 + 3 * 2));
+	op.flops = 2.0 * nb * H * W * (64.0 * 128 + 4.0 * 32 * 12);
+	int *err = m_TcError.as<int>();
+	op.run = [launch, err](cudaStream_t st) { return tail_tc_launch(launch, err, st); };
+	plan.push_back(std::move(op));
+	++m_TcOps;
+	if (m_FilterOn) plan.push_back(filterOp(io, preGenNext, bright, b0, nb));
+	plan.push_back(chunkDoneOp(b0, nb));
+}
+
+// Marks streams [b0, b0 + nb) complete: an event that process() makes the copy stream wait on.
+// Inside stream capture it becomes an external event-record node of the frame graph.
+Op Engine::chunkDoneOp(int b0, int nb) {
+	std::size_t idx = 0;
+	for (; idx < m_Chunks.size(); ++idx)
+		if (m_Chunks[idx].first == b0 && m_Chunks[idx].second == nb) break;
+	if (idx == m_Chunks.size()) {
+		cudaEvent_t ev = nullptr;
+		JU_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+		m_Chunks.emplace_back(b0, nb);
+		m_ChunkDone.push_back(ev);
+	}
+	cudaEvent_t ev = m_ChunkDone[idx];
+	Op op;
+	op.name = "sync:streams_done";
+	op.kernels = 0;
+	op.layers = 0;
+	op.run = [ev](cudaStream_t st) {
+		cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+		cudaError_t e = cudaStreamIsCapturing(st, &status);
+		if (e != cudaSuccess) return e;
+		return cudaEventRecordWithFlags(ev, st,
+		    status == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault);
+	};
+	return op;
 }
 
 // frame_moving_avg.py:142-307: blend the generator output (left in m_OutRaw by the tail kernel,
 // un-normalised) with the warped previous output still sitting in the generator input tensor;
 // rewrites the u8 image and produces the recurrent state
-Op Engine::filterOp(const FrameIO *io, __half *preGenNext, const float *bright) {
-	const int B = m_Batch, H = m_Spec.frameH, W = m_Spec.frameW;
+// for streams [b0, b0 + nb); io / preGenNext / bright already point at stream b0
+Op Engine::filterOp(const FrameIO *io, __half *preGenNext, const float *bright, int b0, int nb) {
+	const int B = nb, H = m_Spec.frameH, W = m_Spec.frameW;
 	Op op;
 	op.name = "frame_moving_avg";
 	op.kernels = m_Filter.window == 0 ? 3 : 2;
 	// two passes over out (4 x fp16) and pw (fp16) + u8 image + fp16 state
 	op.bytes = static_cast<double>(B) * (2.0 * (16.0 * H * W * 8 + H * W * 128.0) + 16.0 * H * W * (4 + 8));
-	const __half *outRaw = m_OutRaw.as<__half>();
-	const __half *genIn = m_GenIn.as<__half>();
-	float *scratch = m_FilterScratch.as<float>();
+	const __half *outRaw = m_OutRaw.as<__half>() + static_cast<std::size_t>(16) * H * W * 4 * b0;
+	const __half *genIn = m_GenIn.as<__half>() + static_cast<std::size_t>(H) * W * 64 * b0;
+	float *scratch = m_FilterScratch.as<float>() + m_FilterScratchPerStream * b0;
 	const FilterParams fp = m_Filter;
 	op.run = [=](cudaStream_t st) {
 		return launch_frame_filter(outRaw, genIn, io, preGenNext, bright, scratch, fp, B, H, W, st);
@@ -729,19 +789,34 @@ void Engine::process(int n, const ju_image *inputs, const ju_image *outputs) {
 		} else {
 			for (const Op &op : m_Plans[m_Parity]) checkCuda(op.run(m_Stream), op.name.c_str());
 		}
-		for (int s = 0; s < n; ++s) {
-			if (!m_OutputNeedsCopy[s]) continue;
-			const ju_image &out = outputs[s];
-			const std::uint8_t *stage = m_OutStage.as<std::uint8_t>() + s * 4 * H * outRow;
-			auto *p = static_cast<std::uint8_t *>(out.ptr);
-			if (out.stride >= 0) {
-				JU_CUDA(cudaMemcpy2DAsync(p, out.stride, stage, outRow, outRow, 4 * H, cudaMemcpyDeviceToHost, m_Stream));
-			} else {
-				std::uint8_t *lowest = p + static_cast<std::int64_t>(4 * H - 1) * out.stride;
-				JU_CUDA(cudaMemcpy2DAsync(lowest, -out.stride, stage, outRow, outRow, 4 * H, cudaMemcpyDeviceToHost, m_Stream));
+		// Device-to-host copies of staged images run on a second stream, one group of streams at a
+		// time as soon as the frame graph has recorded that group's completion event: with several
+		// sub-batches the copies of the first streams overlap the trunk of the later ones.
+		bool copied = false;
+		for (std::size_t c = 0; c < m_Chunks.size(); ++c) {
+			const int b0 = m_Chunks[c].first, b1 = std::min(n, b0 + m_Chunks[c].second);
+			bool any = false;
+			for (int s = b0; s < b1; ++s) any = any || m_OutputNeedsCopy[s];
+			if (!any) continue;
+			JU_CUDA(cudaStreamWaitEvent(m_CopyStream, m_ChunkDone[c], 0));
+			for (int s = b0; s < b1; ++s) {
+				if (!m_OutputNeedsCopy[s]) continue;
+				const ju_image &out = outputs[s];
+				const std::uint8_t *stage = m_OutStage.as<std::uint8_t>() + s * 4 * H * outRow;
+				auto *p = static_cast<std::uint8_t *>(out.ptr);
+				if (out.stride >= 0) {
+					JU_CUDA(cudaMemcpy2DAsync(p, out.stride, stage, outRow, outRow, 4 * H, cudaMemcpyDeviceToHost,
+					    m_CopyStream));
+				} else {
+					std::uint8_t *lowest = p + static_cast<std::int64_t>(4 * H - 1) * out.stride;
+					JU_CUDA(cudaMemcpy2DAsync(lowest, -out.stride, stage, outRow, outRow, 4 * H,
+					    cudaMemcpyDeviceToHost, m_CopyStream));
+				}
+				copied = true;
 			}
 		}
 		JU_CUDA(cudaStreamSynchronize(m_Stream));
+		if (copied) JU_CUDA(cudaStreamSynchronize(m_CopyStream));
 	} catch (...) {
 		// a failed frame leaves the ping-pong index unchanged (the reference
 		// flips only after the synchronize, tensorrt_backend.cc:276-277)
@@ -832,6 +907,7 @@ std::vector<ju_op_time> Engine::profileOps(int iters) {
 	auto groupOf = [](const std::string &n) -> std::string {
 		if (n.rfind("generator/block_", 0) == 0) return "resblocks";
 		if (n.rfind("flow/", 0) == 0) return "flow";
+		if (n.rfind("sync:", 0) == 0) return "sync";
 		return n;
 	};
 	std::vector<std::string> labels;
@@ -885,19 +961,27 @@ std::vector<ju_op_time> Engine::profileOps(int iters) {
 		throw;
 	}
 	destroyExecs();
+	// a label can occur several times in the plan (per sub-batch trunk / tail): one entry per label
+	std::vector<std::string> unique;
 	for (std::size_t g = 0; g < labels.size(); ++g) {
-		ju_op_time o;
-		std::memset(&o, 0, sizeof(o));
-		std::snprintf(o.name, sizeof(o.name), "group:%s", labels[g].c_str());
-		o.usec = gtotal[g] / iters;
+		std::size_t u = 0;
+		for (; u < unique.size(); ++u)
+			if (unique[u] == labels[g]) break;
+		if (u == unique.size()) {
+			unique.push_back(labels[g]);
+			ju_op_time o;
+			std::memset(&o, 0, sizeof(o));
+			std::snprintf(o.name, sizeof(o.name), "group:%s", labels[g].c_str());
+			result.push_back(o);
+		}
+		ju_op_time &o = result[plan.size() + u];
+		o.usec += gtotal[g] / iters;
 		for (std::size_t i = firstOp[g]; i < firstOp[g + 1]; ++i) {
 			o.flops += plan[i].flops;
 			o.bytes += plan[i].bytes;
 			o.tensor_bound |= plan[i].tensorBound ? 1 : 0;
+			o.reserved += plan[i].layers;
 		}
-		o.reserved = 0;
-		for (std::size_t i = firstOp[g]; i < firstOp[g + 1]; ++i) o.reserved += plan[i].layers;
-		result.push_back(o);
 	}
 	for (auto &e : ev) cudaEventDestroy(e);
 	return result;

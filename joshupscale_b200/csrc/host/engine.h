@@ -86,7 +86,9 @@ private:
 	void buildPlan(int parity);
 	void capture(int parity);
 	ConvLayer *addConv(const std::string &name, const FoldedConv &f, int act, float slope, bool shuffle2);
-	Op filterOp(const FrameIO *io, __half *preGenNext, const float *bright);
+	Op filterOp(const FrameIO *io, __half *preGenNext, const float *bright, int b0, int nb);
+	void emitTail(std::vector<Op> &plan, int parity, const __half *trunkOut, int gs, int b0, int nb);
+	Op chunkDoneOp(int b0, int nb);
 	Op convOp(ConvLayer *layer, const __half *in, int cinStride, const __half *residual, void *out,
 	    int coutStride, int h, int w, bool outF32, bool pool = false);
 	DeviceBuffer &newActivation(std::size_t bytes);
@@ -120,6 +122,11 @@ private:
 	bool m_FilterOn = false;
 	FilterParams m_Filter{};
 	DeviceBuffer m_OutRaw, m_FilterScratch;
+	std::size_t m_FilterScratchPerStream = 0;
+	// streams [first, first + second) whose images are complete when the matching event fires
+	std::vector<std::pair<int, int>> m_Chunks;
+	std::vector<cudaEvent_t> m_ChunkDone;
+	cudaStream_t m_CopyStream = nullptr;
 	std::vector<std::unique_ptr<DeviceBuffer>> m_Activations;
 	std::vector<std::unique_ptr<ConvLayer>> m_Layers;
 	std::map<std::string, ConvLayer *> m_LayerByName;

@@ -338,3 +338,27 @@ def test_pinned_and_pageable_host_outputs_agree(tmp_path):
                 assert (pinned[:, ow * 4:] == 0xAB).all()
     finally:
         jrt._check(lib.ju_host_free(p_out))
+
+
+@pytest.mark.parametrize("with_filter", [False, True])
+def test_sub_batched_streams_with_overlapped_copies_equal_single_streams(tmp_path, with_filter):
+    """Batch 5 at full size runs as trunk/tail sub-batches (2 + 2 + 1 streams) whose images are copied
+    to the host on a second stream as each sub-batch finishes; every stream must still equal its own
+    single-stream run, frame after frame (host images, so the staged-copy path is exercised)."""
+    from joshupscale_b200 import config as jcfg, weights as jw
+    import os
+    cfg = jcfg.preset("psp_fast")
+    w = jw.init_weights(cfg, 42, True)
+    flt = jcfg.OutputFilter(window=32, threshold=0.2) if with_filter else None
+    path = os.path.join(str(tmp_path), "m.jup")
+    jw.save_model(path, cfg, jw.with_output_filter(w, flt))
+    n, frames = 5, 3
+    clips = [synthetic.frames(cfg.frame_height, cfg.frame_width, frames, stream_id=s,
+                              kind="cut" if s % 2 else "pan") for s in range(n)]
+    with jrt.Runtime(path, 0, n) as rt:
+        batched = [rt.process_batch([c[t] for c in clips]) for t in range(frames)]
+        batched = [[o.copy() for o in outs] for outs in batched]
+    for s in (0, 3, 4):
+        with jrt.Runtime(path, 0, 1) as one:
+            for t in range(frames):
+                np.testing.assert_array_equal(batched[t][s], one.process(clips[s][t]))
