@@ -68,24 +68,34 @@ Engine::Engine(const ModelFile &model, int device, int batch)
 			}
 		}
 		allocate();
-		buildPlan(0);
-		buildPlan(1);
+		buildPlan(0, 0);
+		buildPlan(1, 0);
+		// Second plan for frames whose images live in host memory: at batch 1 the tail kernel runs
+		// as JU_TAIL_BANDS bands of tile rows, each followed by a completion event, so the 8 MB
+		// device-to-host copy starts after the first band instead of after the whole frame.
+		m_TailBands = envInt("JU_TAIL_BANDS", 3);
+		m_HostVariant = m_TailBands > 1 && m_Batch == 1 && !m_FilterOn;
+		if (m_HostVariant) {
+			buildPlan(0, 1);
+			buildPlan(1, 1);
+			m_HostVariant = m_Regions[1].size() > 1;  // the plan may not have been able to band the tail
+		}
 		if (m_UseGraph) {
-			capture(0);
-			capture(1);
+			for (int v = 0; v < (m_HostVariant ? 2 : 1); ++v) {
+				capture(0, v);
+				capture(1, v);
+			}
 		}
 		JU_CUDA(cudaStreamSynchronize(m_Stream));
 	} catch (...) {
-		for (auto &g : m_GraphExec)
-			if (g) cudaGraphExecDestroy(g);
-		for (auto &e : m_ChunkDone) cudaEventDestroy(e);
+		destroyGraphsAndEvents();
 		cudaStreamDestroy(m_CopyStream);
 		cudaStreamDestroy(m_Stream);
 		throw;
 	}
 	JU_LOG_INFO << "engine ready: " << m_Spec.frameW << "x" << m_Spec.frameH << " -> "
 	            << 4 * m_Spec.frameW << "x" << 4 * m_Spec.frameH << ", batch " << m_Batch << ", "
-	            << m_Plans[0].size() << " kernels/frame, conv impl " << m_ConvImpl << " (" << m_TcOps / 2
+	            << m_Plans[0][0].size() << " kernels/frame, conv impl " << m_ConvImpl << " (" << m_TcOps / 2
 	            << " tcgen05 launches/frame)";
 }
 
@@ -93,11 +103,22 @@ Engine::~Engine() {
 	cudaSetDevice(m_Device);
 	cudaStreamSynchronize(m_Stream);
 	cudaStreamSynchronize(m_CopyStream);
-	for (auto &g : m_GraphExec)
-		if (g) cudaGraphExecDestroy(g);
-	for (auto &e : m_ChunkDone) cudaEventDestroy(e);
+	destroyGraphsAndEvents();
 	cudaStreamDestroy(m_CopyStream);
 	cudaStreamDestroy(m_Stream);
+}
+
+void Engine::destroyGraphsAndEvents() {
+	for (auto &pair : m_GraphExec)
+		for (auto &g : pair)
+			if (g) {
+				cudaGraphExecDestroy(g);
+				g = nullptr;
+			}
+	for (auto &regions : m_Regions) {
+		for (Region &r : regions) cudaEventDestroy(r.ev);
+		regions.clear();
+	}
 }
 
 // ---------------------------------------------------------------------------
@@ -326,14 +347,15 @@ Op Engine::convOp(ConvLayer *L, const __half *in, int cinStride, const __half *r
 	return op;
 }
 
-void Engine::buildPlan(int parity) {
+void Engine::buildPlan(int parity, int variant) {
+	m_BuildVariant = variant;
 	const ModelSpec &s = m_Spec;
 	const int B = m_Batch, H = s.frameH, W = s.frameW, PH = s.padH, PW = s.padW;
-	std::vector<Op> &plan = m_Plans[parity];
+	std::vector<Op> &plan = m_Plans[variant][parity];
 	plan.clear();
 	std::size_t actCursor = 0;
 	auto activation = [&](std::size_t bytes) -> __half * {
-		if (parity == 0) return newActivation(bytes).as<__half>();
+		if (parity == 0 && variant == 0) return newActivation(bytes).as<__half>();
 		DeviceBuffer &buf = *m_Activations.at(actCursor++);
 		if (buf.bytes() != bytes) throw std::logic_error("activation plan mismatch");
 		return buf.as<__half>();
@@ -598,7 +620,7 @@ void Engine::buildPlan(int parity) {
 		plan.push_back(std::move(op));
 	}
 	if (m_FilterOn) plan.push_back(filterOp(io, preGenNext, bright, 0, B));
-	plan.push_back(chunkDoneOp(0, B));
+	plan.push_back(chunkDoneOp(0, B, 0, 4 * H));
 }
 
 // Fused tail (+ output filter) for streams [b0, b0 + nb), followed by the event that tells
@@ -628,35 +650,50 @@ void Engine::emitTail(std::vector<Op> &plan, int parity, const __half *trunkOut,
 	ta.act = ct1->act;
 	ta.slope = ct1->slope;
 	ta.pdl = 1;
-	TailTcLaunch launch;
-	checkCuda(tail_tc_prepare(ta, &launch), "tail_tc_prepare");
-	Op op;
-	op.name = "tail_fused";
-	op.tensorBound = false;
-	// read trunk (64ch fp16) + LR input + write BGRX u8 + fp16 state (3ch), SURVEY 8(d)
-	op.bytes = static_cast<double>(nb) * (H * W * 64 * 2.0 + H * W * 4.0 + 16.0 * H * W * (4 + 3 * 2));
-	op.flops = 2.0 * nb * H * W * (64.0 * 128 + 4.0 * 32 * 12);
 	int *err = m_TcError.as<int>();
-	op.run = [launch, err](cudaStream_t st) { return tail_tc_launch(launch, err, st); };
-	plan.push_back(std::move(op));
-	++m_TcOps;
+	const int tileRows = (H + 15) / 16;
+	const int bands = (m_BuildVariant == 1 && nb == 1 && m_Batch == 1 && !m_FilterOn) ? std::min(m_TailBands, tileRows) : 1;
+	for (int band = 0; band < bands; ++band) {
+		const int r0 = tileRows * band / bands, r1 = tileRows * (band + 1) / bands;
+		TailArgs tb = ta;
+		if (bands > 1) {
+			tb.tile_row_begin = r0;
+			tb.tile_row_end = r1;
+		}
+		TailTcLaunch launch;
+		checkCuda(tail_tc_prepare(tb, &launch), "tail_tc_prepare");
+		const double share = static_cast<double>(r1 - r0) / tileRows;
+		Op op;
+		op.name = "tail_fused";
+		op.tensorBound = false;
+		// read trunk (64ch fp16) + LR input + write BGRX u8 + fp16 state (3ch), SURVEY 8(d)
+		op.bytes = share * nb * (H * W * 64 * 2.0 + H * W * 4.0 + 16.0 * H * W * (4 + 3 * 2));
+		op.flops = share * 2.0 * nb * H * W * (64.0 * 128 + 4.0 * 32 * 12);
+		op.run = [launch, err](cudaStream_t st) { return tail_tc_launch(launch, err, st); };
+		plan.push_back(std::move(op));
+		++m_TcOps;
+		if (bands > 1) plan.push_back(chunkDoneOp(b0, nb, 64 * r0, std::min(64 * r1, 4 * H)));
+	}
+	if (bands > 1) return;
 	if (m_FilterOn) plan.push_back(filterOp(io, preGenNext, bright, b0, nb));
-	plan.push_back(chunkDoneOp(b0, nb));
+	plan.push_back(chunkDoneOp(b0, nb, 0, 4 * H));
 }
 
 // Marks streams [b0, b0 + nb) complete: an event that process() makes the copy stream wait on.
 // Inside stream capture it becomes an external event-record node of the frame graph.
-Op Engine::chunkDoneOp(int b0, int nb) {
+Op Engine::chunkDoneOp(int b0, int nb, int row0, int row1) {
+	std::vector<Region> &regions = m_Regions[m_BuildVariant];
 	std::size_t idx = 0;
-	for (; idx < m_Chunks.size(); ++idx)
-		if (m_Chunks[idx].first == b0 && m_Chunks[idx].second == nb) break;
-	if (idx == m_Chunks.size()) {
-		cudaEvent_t ev = nullptr;
-		JU_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-		m_Chunks.emplace_back(b0, nb);
-		m_ChunkDone.push_back(ev);
+	for (; idx < regions.size(); ++idx) {
+		const Region &r = regions[idx];
+		if (r.b0 == b0 && r.nb == nb && r.row0 == row0 && r.row1 == row1) break;
 	}
-	cudaEvent_t ev = m_ChunkDone[idx];
+	if (idx == regions.size()) {  // both parities share the events
+		Region r{b0, nb, row0, row1, nullptr};
+		JU_CUDA(cudaEventCreateWithFlags(&r.ev, cudaEventDisableTiming));
+		regions.push_back(r);
+	}
+	cudaEvent_t ev = regions[idx].ev;
 	Op op;
 	op.name = "sync:streams_done";
 	op.kernels = 0;
@@ -692,18 +729,18 @@ Op Engine::filterOp(const FrameIO *io, __half *preGenNext, const float *bright, 
 	return op;
 }
 
-void Engine::capture(int parity) {
+void Engine::capture(int parity, int variant) {
 	cudaGraph_t graph = nullptr;
 	JU_CUDA(cudaStreamBeginCapture(m_Stream, cudaStreamCaptureModeThreadLocal));
 	cudaError_t err = cudaSuccess;
-	for (const Op &op : m_Plans[parity]) {
+	for (const Op &op : m_Plans[variant][parity]) {
 		err = op.run(m_Stream);
 		if (err != cudaSuccess) break;
 	}
 	cudaError_t endErr = cudaStreamEndCapture(m_Stream, &graph);
 	checkCuda(err, "kernel launch during graph capture");
 	checkCuda(endErr, "cudaStreamEndCapture");
-	cudaError_t instErr = cudaGraphInstantiate(&m_GraphExec[parity], graph, 0);
+	cudaError_t instErr = cudaGraphInstantiate(&m_GraphExec[variant][parity], graph, 0);
 	cudaGraphDestroy(graph);
 	checkCuda(instErr, "cudaGraphInstantiate");
 }
@@ -784,33 +821,40 @@ void Engine::process(int n, const ju_image *inputs, const ju_image *outputs) {
 	const std::size_t H = m_Spec.frameH, W = m_Spec.frameW, outRow = 4 * W * 4;
 	try {
 		bindImages(n, inputs, outputs);
+		bool anyCopy = false;
+		for (int s = 0; s < n; ++s) anyCopy = anyCopy || m_OutputNeedsCopy[s];
+		const int variant = (m_HostVariant && anyCopy) ? 1 : 0;
 		if (m_UseGraph) {
-			JU_CUDA(cudaGraphLaunch(m_GraphExec[m_Parity], m_Stream));
+			JU_CUDA(cudaGraphLaunch(m_GraphExec[variant][m_Parity], m_Stream));
 		} else {
-			for (const Op &op : m_Plans[m_Parity]) checkCuda(op.run(m_Stream), op.name.c_str());
+			for (const Op &op : m_Plans[variant][m_Parity]) checkCuda(op.run(m_Stream), op.name.c_str());
 		}
 		// Device-to-host copies of staged images run on a second stream, one group of streams at a
 		// time as soon as the frame graph has recorded that group's completion event: with several
 		// sub-batches the copies of the first streams overlap the trunk of the later ones.
 		bool copied = false;
-		for (std::size_t c = 0; c < m_Chunks.size(); ++c) {
-			const int b0 = m_Chunks[c].first, b1 = std::min(n, b0 + m_Chunks[c].second);
+		for (const Region &r : m_Regions[variant]) {
+			const int b0 = r.b0, b1 = std::min(n, r.b0 + r.nb);
 			bool any = false;
 			for (int s = b0; s < b1; ++s) any = any || m_OutputNeedsCopy[s];
 			if (!any) continue;
-			JU_CUDA(cudaStreamWaitEvent(m_CopyStream, m_ChunkDone[c], 0));
+			JU_CUDA(cudaStreamWaitEvent(m_CopyStream, r.ev, 0));
+			const std::size_t rows = static_cast<std::size_t>(r.row1 - r.row0);
 			for (int s = b0; s < b1; ++s) {
 				if (!m_OutputNeedsCopy[s]) continue;
 				const ju_image &out = outputs[s];
 				const std::uint8_t *stage = m_OutStage.as<std::uint8_t>() + s * 4 * H * outRow;
 				auto *p = static_cast<std::uint8_t *>(out.ptr);
 				if (out.stride >= 0) {
-					JU_CUDA(cudaMemcpy2DAsync(p, out.stride, stage, outRow, outRow, 4 * H, cudaMemcpyDeviceToHost,
-					    m_CopyStream));
+					JU_CUDA(cudaMemcpy2DAsync(p + static_cast<std::int64_t>(r.row0) * out.stride, out.stride,
+					    stage + r.row0 * outRow, outRow, outRow, rows, cudaMemcpyDeviceToHost, m_CopyStream));
 				} else {
+					// bottom-up: image row i lives in memory row 4H-1-i of both the staging buffer and the
+					// caller's buffer, so image rows [row0, row1) are memory rows [4H-row1, 4H-row0)
+					const std::size_t m0 = 4 * H - static_cast<std::size_t>(r.row1);
 					std::uint8_t *lowest = p + static_cast<std::int64_t>(4 * H - 1) * out.stride;
-					JU_CUDA(cudaMemcpy2DAsync(lowest, -out.stride, stage, outRow, outRow, 4 * H,
-					    cudaMemcpyDeviceToHost, m_CopyStream));
+					JU_CUDA(cudaMemcpy2DAsync(lowest + m0 * static_cast<std::size_t>(-out.stride), -out.stride,
+					    stage + m0 * outRow, outRow, outRow, rows, cudaMemcpyDeviceToHost, m_CopyStream));
 				}
 				copied = true;
 			}
@@ -869,7 +913,7 @@ std::vector<ju_op_time> Engine::profileOps(int iters) {
 	if (iters < 1) iters = 1;
 	DeviceGuard guard(m_Device);
 	JU_CUDA(cudaStreamSynchronize(m_Stream));
-	const std::vector<Op> &plan = m_Plans[m_Parity];
+	const std::vector<Op> &plan = m_Plans[0][m_Parity];
 	std::vector<cudaEvent_t> ev(plan.size() + 1);
 	for (auto &e : ev) JU_CUDA(cudaEventCreate(&e));
 	std::vector<double> total(plan.size(), 0.0);

@@ -69,7 +69,7 @@ public:
 	int convImpl() const { return m_ConvImpl; }
 	std::size_t kernelsPerFrame() const {
 		std::size_t n = 0;
-		for (const Op &op : m_Plans[0]) n += static_cast<std::size_t>(op.kernels);
+		for (const Op &op : m_Plans[0][0]) n += static_cast<std::size_t>(op.kernels);
 		return n;
 	}
 
@@ -83,12 +83,13 @@ public:
 private:
 	void buildLayers(const ModelFile &model);
 	void allocate();
-	void buildPlan(int parity);
-	void capture(int parity);
+	void buildPlan(int parity, int variant);
+	void capture(int parity, int variant);
+	void destroyGraphsAndEvents();
 	ConvLayer *addConv(const std::string &name, const FoldedConv &f, int act, float slope, bool shuffle2);
 	Op filterOp(const FrameIO *io, __half *preGenNext, const float *bright, int b0, int nb);
 	void emitTail(std::vector<Op> &plan, int parity, const __half *trunkOut, int gs, int b0, int nb);
-	Op chunkDoneOp(int b0, int nb);
+	Op chunkDoneOp(int b0, int nb, int row0, int row1);
 	Op convOp(ConvLayer *layer, const __half *in, int cinStride, const __half *residual, void *out,
 	    int coutStride, int h, int w, bool outF32, bool pool = false);
 	DeviceBuffer &newActivation(std::size_t bytes);
@@ -105,7 +106,7 @@ private:
 	bool m_Conv2Cta = false;
 	int m_Parity = 0;
 	cudaStream_t m_Stream = nullptr;
-	cudaGraphExec_t m_GraphExec[2] = {nullptr, nullptr};
+	cudaGraphExec_t m_GraphExec[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [variant][parity]
 
 	PinnedBuffer m_IoHost;
 	DeviceBuffer m_IoDev;
@@ -123,14 +124,22 @@ private:
 	FilterParams m_Filter{};
 	DeviceBuffer m_OutRaw, m_FilterScratch;
 	std::size_t m_FilterScratchPerStream = 0;
-	// streams [first, first + second) whose images are complete when the matching event fires
-	std::vector<std::pair<int, int>> m_Chunks;
-	std::vector<cudaEvent_t> m_ChunkDone;
+	// output rows [row0, row1) of streams [b0, b0 + nb) are complete when `ev` fires
+	struct Region {
+		int b0, nb, row0, row1;
+		cudaEvent_t ev;
+	};
+	// plan variant 0: the frame as one pass (device-resident images); variant 1 (batch 1, host
+	// images): tail kernel in bands so that the device-to-host copy overlaps it
+	std::vector<Region> m_Regions[2];
+	int m_BuildVariant = 0;
+	int m_TailBands = 1;
+	bool m_HostVariant = false;
 	cudaStream_t m_CopyStream = nullptr;
 	std::vector<std::unique_ptr<DeviceBuffer>> m_Activations;
 	std::vector<std::unique_ptr<ConvLayer>> m_Layers;
 	std::map<std::string, ConvLayer *> m_LayerByName;
-	std::vector<Op> m_Plans[2];
+	std::vector<Op> m_Plans[2][2];  // [variant][parity]
 	std::map<std::string, NamedTensor> m_Tensors;
 	int m_FlowCStride = 64;
 };

@@ -113,6 +113,7 @@ struct TailArgs {
 	int act;
 	float slope;
 	int pdl;
+	int tile_row_begin, tile_row_end;  // optional band of 16-row tile rows (batch 1 only); 0, 0 = everything
 };
 struct TailTcLaunch {
 	alignas(64) unsigned char map_a[128];

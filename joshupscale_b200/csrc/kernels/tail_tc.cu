@@ -38,6 +38,7 @@ constexpr uint32_t kBBytes = 128u * 128u; // 128 output channels x 64 ch fp16
 struct TailParams {
 	int batch, h, w;
 	int tiles_x, tiles_y, total_tiles;
+	int tile_begin;  // first tile of this launch (a launch may cover a band of tile rows only)
 	int act;
 	float slope;
 	int pdl;
@@ -141,7 +142,7 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 			tma_load_2d(b_base, &map_b, w_bar, 0, 0);
 			if (p.pdl) grid_dependency_wait();
 			int it = 0;
-			for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+			for (int tile = p.tile_begin + blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
 				int b, y0, x0;
 				decode(tile, b, y0, x0);
 				const int s = it % kStages;
@@ -158,7 +159,7 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 			const uint32_t lo_flags = 1u << 16;
 			mbar_wait(w_bar, 0, p.error_flag, 2);
 			int it = 0;
-			for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+			for (int tile = p.tile_begin + blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
 				const int as = it & 1;
 				const uint32_t aph = (it >> 1) & 1;
 				mbar_wait(tempty_bar(as), aph ^ 1u, p.error_flag, 3);
@@ -194,7 +195,7 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 		if (p.pdl) grid_dependency_wait();
 		const int H4 = 4 * p.h, W4 = 4 * p.w;
 		int it = 0;
-		for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+		for (int tile = p.tile_begin + blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
 			int b, y0, x0;
 			decode(tile, b, y0, x0);
 			const int as = it & 1;
@@ -354,6 +355,13 @@ cudaError_t tail_tc_prepare(const TailArgs &a, TailTcLaunch *out) {
 	p.tiles_x = (a.w + kTileW - 1) / kTileW;
 	p.tiles_y = (a.h + kTileH - 1) / kTileH;
 	p.total_tiles = a.batch * p.tiles_x * p.tiles_y;
+	p.tile_begin = 0;
+	if (a.tile_row_end > a.tile_row_begin) {
+		// a band of tile rows (single stream): tiles are numbered row-major
+		if (a.batch != 1 || a.tile_row_end > p.tiles_y || a.tile_row_begin < 0) return cudaErrorInvalidValue;
+		p.tile_begin = a.tile_row_begin * p.tiles_x;
+		p.total_tiles = a.tile_row_end * p.tiles_x;
+	}
 	p.act = a.act;
 	p.slope = a.slope;
 	p.pdl = a.pdl;
@@ -396,7 +404,8 @@ cudaError_t tail_tc_prepare(const TailArgs &a, TailTcLaunch *out) {
 	int dev = 0, sms = 148;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-	out->grid = p.total_tiles < sms ? p.total_tiles : sms;
+	const int n_tiles = p.total_tiles - p.tile_begin;
+	out->grid = n_tiles < sms ? n_tiles : sms;
 	out->smem_bytes = kSmemBytes;
 	out->pdl = a.pdl;
 	return cudaSuccess;

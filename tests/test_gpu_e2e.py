@@ -362,3 +362,32 @@ def test_sub_batched_streams_with_overlapped_copies_equal_single_streams(tmp_pat
         with jrt.Runtime(path, 0, 1) as one:
             for t in range(frames):
                 np.testing.assert_array_equal(batched[t][s], one.process(clips[s][t]))
+
+
+def test_banded_tail_for_host_images_matches_device_resident_run(tmp_path):
+    """At batch 1 frames with host images run the tail kernel in bands with overlapped row-band
+    copies; device-resident images run it in one pass.  Same bytes either way, also for bottom-up
+    host images, and the recurrent state stays in step when the two kinds of call alternate."""
+    import ctypes as C
+    cfg, _, path = make_model(tmp_path, "psp_fast")
+    h, w = cfg.frame_height, cfg.frame_width
+    oh, ow = 4 * h, 4 * w
+    frames = synthetic.frames(h, w, 4)
+    lib = jrt.load_library()
+    d_in, d_out = jk.DeviceArray((h, w, 4), np.uint8), jk.DeviceArray((oh, ow, 4), np.uint8)
+    with jrt.Runtime(path, 0, 1) as host_rt, jrt.Runtime(path, 0, 1) as dev_rt:
+        for t, f in enumerate(frames):
+            d_in.upload(np.ascontiguousarray(f))
+            dev_rt.process_images([jrt.JuImage(d_in.ptr, jrt.LOC_CUDA, w * 4, w, h)],
+                                  [jrt.JuImage(d_out.ptr, jrt.LOC_CUDA, ow * 4, ow, oh)])
+            want = d_out.download()
+            if t % 2 == 0:
+                got = host_rt.process(f)
+            else:  # bottom-up host image: pointer to the last memory row, negative stride
+                buf = np.full((oh, ow, 4), 0xCD, np.uint8)
+                src = np.ascontiguousarray(f[::-1])
+                host_rt.process_images(
+                    [jrt.JuImage(src.ctypes.data + (h - 1) * w * 4, jrt.LOC_CPU, -w * 4, w, h)],
+                    [jrt.JuImage(buf.ctypes.data + (oh - 1) * ow * 4, jrt.LOC_CPU, -ow * 4, ow, oh)])
+                got = buf[::-1]
+            np.testing.assert_array_equal(got, want)
