@@ -222,3 +222,47 @@ def test_dataflow_trunk_race_stress(tmp_path):
         finally:
             os.environ.pop("JU_FUSED_TRUNK", None)
         np.testing.assert_array_equal(first, ref)
+
+
+@pytest.mark.parametrize("env", [
+    {"JU_NO_GRAPH": "1"},
+    {"JU_TC_DUAL": "0"},
+    {"JU_TC_PDL": "0"},
+    {"JU_FUSED_POOL": "0"},
+    {"JU_TRUNK_SUBBATCH": "0"},
+    {"JU_TRUNK_SUBBATCH": "1"},
+    {"JU_TAIL_BANDS": "1"},
+    {"JU_TAIL_BANDS": "5", "JU_NO_GRAPH": "1"},
+])
+def test_execution_switches_do_not_change_the_bytes(tmp_path, env):
+    """Scheduling / fusion switches only change HOW the frame is executed:
+    the output bytes of a 3-stream, 3-frame run must equal the default configuration's."""
+    cfg, _, path = make_model(tmp_path, "psp_fast")
+    clips = [synthetic.frames(cfg.frame_height, cfg.frame_width, 3, stream_id=s) for s in range(3)]
+
+    def run():
+        with jrt.Runtime(path, 0, 3) as rt:
+            batched = [[o.copy() for o in rt.process_batch([c[t] for c in clips])] for t in range(3)]
+        with jrt.Runtime(path, 0, 1) as rt:  # batch 1: banded-tail host path
+            single = [rt.process(clips[0][t]).copy() for t in range(3)]
+        return batched, single
+
+    want_b, want_s = run()
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        got_b, got_s = run()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+        # the conv_tc switches are process-global once set: back to their defaults
+        jrt.set_option("tc_dual", 1)
+        jrt.set_option("tc_pdl", 1)
+    for t in range(3):
+        np.testing.assert_array_equal(got_s[t], want_s[t])
+        np.testing.assert_array_equal(want_s[t], want_b[t][0])
+        for s in range(3):
+            np.testing.assert_array_equal(got_b[t][s], want_b[t][s])
