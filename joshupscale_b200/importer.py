@@ -2,8 +2,9 @@
 
 The reference trains with Keras 3 and checkpoints `*.weights.h5`
 (scripts/training/train_local.py:119-128, 188); its layers carry the names used
-throughout this package (scripts/training/models.py: `block_<i>/conv_<j>`,
-`bn_<j>`, `conv_trans_<j>` inside a flow model and a generator model).  This
+throughout this package (scripts/training/models.py: `block_<i>_conv_<j>`, `block_<i>_bn_<j>`,
+`conv_<j>`, `bn_<j>`, `conv_trans_<j>` inside a flow model and a generator model;
+the container spells the block scope with a slash, `block_<i>/conv_<j>`).  This
 tool takes either
 
   * an `.npz` whose keys are Keras variable paths, e.g. written where TensorFlow
@@ -65,13 +66,19 @@ def _split(parts: List[str]) -> Optional[Tuple[Optional[str], str]]:
     if var not in ("kernel", "bias") + _BN_VARS:
         return None
     layer = parts[-2] if len(parts) > 1 else ""
-    if not re.fullmatch(r"(conv|bn|conv_trans)_\d+", layer):
-        return None
-    rel = [layer, var]
     rest = parts[:-2]
-    if rest and re.fullmatch(r"block_\d+", rest[-1]):
-        rel.insert(0, rest[-1])
-        rest = rest[:-1]
+    # the reference scopes block layers with an underscore (models.py get_scoped_name):
+    # "block_3_conv_1"; "block_3/conv_1" is accepted as well
+    m = re.fullmatch(r"(block_\d+)_((?:conv|bn)_\d+)", layer)
+    if m:
+        rel = [m.group(1), m.group(2), var]
+    elif re.fullmatch(r"(conv|bn|conv_trans)_\d+", layer):
+        rel = [layer, var]
+        if rest and re.fullmatch(r"block_\d+", rest[-1]):
+            rel.insert(0, rest[-1])
+            rest = rest[:-1]
+    else:
+        return None
     return _scope_kind(rest), "/".join(rel)
 
 

@@ -391,3 +391,21 @@ def test_banded_tail_for_host_images_matches_device_resident_run(tmp_path):
                     [jrt.JuImage(buf.ctypes.data + (oh - 1) * ow * 4, jrt.LOC_CPU, -ow * 4, ow, oh)])
                 got = buf[::-1]
             np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny_default_init", "small_bright", "small_resnet"])
+def test_engine_matches_vectors_from_the_reference_built_graph(tmp_path, name):
+    """tests/golden/graph_golden.npz comes from executing the reference's own models.py /
+    keras_layers.py / tfa under a shim (tests/golden/make_graph_golden.py): the CUDA engine must
+    match it within the north-star tolerance, without the oracle in between."""
+    import os
+    from tests.test_graph_golden import CASES, GOLDEN, golden_inputs
+    from joshupscale_b200 import weights as jw
+    gold = np.load(GOLDEN)
+    cfg, w, frames = golden_inputs(name)
+    path = os.path.join(str(tmp_path), "m.jup")
+    jw.save_model(path, cfg, w)
+    got = _run_gpu(path, frames)
+    for t in range(frames.shape[0]):
+        m, _, psnr = u8_stats(got[t, ..., :3], gold[f"{name}/output"][t])
+        assert m <= MAX_ABS_FP32 and psnr >= MIN_PSNR_DB, (name, t, m, psnr)

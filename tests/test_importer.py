@@ -1,5 +1,7 @@
 """Weight importer: Keras variable paths (npz / Keras-3 h5 layout) -> .jup."""
 
+import re
+
 import numpy as np
 import pytest
 
@@ -12,6 +14,8 @@ def _keras_paths(w, flow_scope="final/full/flow_model_1", gen_scope="final/full/
     out = {}
     for k, v in w.items():
         net, rel = k.split("/", 1)
+        # the reference names block layers "block_3_conv_1" (models.py get_scoped_name)
+        rel = re.sub(r"^(block_\d+)/", r"\1_", rel)
         out[f"{flow_scope if net == 'flow' else gen_scope}/{rel}{suffix}"] = v
     # things a training checkpoint also holds and the importer must ignore
     out["discriminator/block_1/conv_1/kernel:0"] = np.zeros((3, 3, 6, 8), np.float32)
@@ -56,6 +60,7 @@ def test_keras3_h5_layout_is_renamed_by_rank():
     for k, v in w.items():
         net, rel = k.split("/", 1)
         layer, var = rel.rsplit("/", 1)
+        layer = layer.replace("/", "_")  # block_3_conv_1, as the reference names its layers
         scope = "layers/flow_model" if net == "flow" else "layers/generator"
         flat[f"{scope}/layers/{layer}/vars/{idx[var]}"] = v
     flat["layers/dense/vars/0"] = np.zeros((4, 1), np.float32)  # not conv / bn: dropped
@@ -69,16 +74,16 @@ def test_keras3_h5_layout_is_renamed_by_rank():
 def test_import_errors_are_specific(tmp_path):
     cfg = jcfg.preset("tiny")
     w = _keras_paths(jw.init_weights(cfg, 1, True))
-    missing = {k: v for k, v in w.items() if "generator_2/block_2/bn_1/beta" not in k}
+    missing = {k: v for k, v in w.items() if "generator_2/block_2_bn_1/beta" not in k}
     with pytest.raises(importer.ImportError_, match="missing variable generator/block_2/bn_1/beta"):
         importer.import_weights(missing, 21, 27)
     bad = dict(w)
-    k = "final/full/flow_model_1/block_2/conv_2/kernel:0"
+    k = "final/full/flow_model_1/block_2_conv_2/kernel:0"
     bad[k] = bad[k][..., :-1]
     with pytest.raises(importer.ImportError_, match="shape"):
         importer.import_weights(bad, 21, 27)
     dup = dict(w)
-    dup["other/flow_model_9/block_1/conv_1/kernel"] = w["final/full/flow_model_1/block_1/conv_1/kernel:0"]
+    dup["other/flow_model_9/block_1/conv_1/kernel"] = w["final/full/flow_model_1/block_1_conv_1/kernel:0"]
     with pytest.raises(importer.ImportError_, match="two source variables"):
         importer.import_weights(dup, 21, 27)
     with pytest.raises(importer.ImportError_, match="no flow / generator"):
