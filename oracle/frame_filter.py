@@ -17,10 +17,14 @@ warped previous output `pre_warp` unless a scene change is detected:
     final = pw * mask + out * mask2                                    (:294-303)
 
 `final` replaces the clip output, so it feeds both Postprocess (u8 image) and
-output_raw (the recurrent pre_gen state).  Parity is unpinned in the same sense
-as the rest of the oracle: the reference has no golden vectors for this script
-and onnx/onnxruntime are not installed here, so ONNX Conv / ReduceMean / Resize
-semantics are restated from their specification.
+output_raw (the recurrent pre_gen state).
+
+Pinning: tests/golden/make_filter_golden.py runs the reference script's main()
+unmodified against recording stand-ins for `onnx` / `graph.Graph` and evaluates
+the op list it builds; tests/test_frame_filter.py checks this module against
+those vectors (structure and constants pinned).  The arithmetic of the ONNX
+operators themselves (Conv, ReduceMean, Resize) is restated from the operator
+specification - onnx / onnxruntime are not installed here.
 """
 
 from __future__ import annotations

@@ -117,3 +117,36 @@ def test_filter_round_trips_through_the_model_container(tmp_path):
     assert jw.FILTER_TENSOR not in jw.with_output_filter(back, None)
     with pytest.raises(ValueError):
         jcfg.OutputFilter(norm="l3").as_vector()
+
+
+# ---- pinned against the reference script itself -----------------------------------------------
+# tests/golden/filter_golden.npz was produced by tests/golden/make_filter_golden.py, which runs
+# /root/reference/scripts/inference/onnx/frame_moving_avg.py main() unmodified against recording
+# stand-ins for onnx / graph.Graph and evaluates the op list it builds.
+
+_GOLDEN_CASES = {
+    "defaults": dict(),
+    "l2_limit": dict(strength=0.5, threshold=0.02, norm="l2", limit=True),
+    "gain_luma": dict(gain=8.0, luma_normalize=True),
+    "window8": dict(window=8, threshold=0.05),
+    "window16_all": dict(window=16, gain=4.0, norm="l2", luma_normalize=True, limit=True, threshold=0.01),
+    "window5": dict(window=5, strength=0.4),
+}
+
+
+@pytest.mark.parametrize("name", sorted(_GOLDEN_CASES))
+def test_oracle_filter_reproduces_the_reference_script(name):
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "filter_golden.npz"))
+    flt = ff.FrameFilter(**_GOLDEN_CASES[name])
+    for k, delta in enumerate((0.02, 0.3)):
+        rng = np.random.default_rng(100 + k)  # same inputs as make_filter_golden.case_inputs
+        pw = rng.uniform(-0.6, 0.6, (1, 36, 44, 3)).astype(np.float32)
+        out = np.clip(pw + rng.normal(0, delta, pw.shape), -0.5, 0.5).astype(np.float32)
+        got = ff.frame_moving_avg(torch.from_numpy(out), torch.from_numpy(pw), flt).numpy()
+        want = gold[f"{name}/{k}"]
+        assert want.shape == got.shape
+        assert np.abs(got - want).max() < 2e-6, (name, k, np.abs(got - want).max())
+        # the gate must have an effect in at least one of the two scenes
+    steady, cut = gold[f"{name}/0"], gold[f"{name}/1"]
+    assert np.abs(steady).max() > 0.1 and np.abs(cut).max() > 0.1
