@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 SCRIPTS = [
     list(range(0, 40)),                                    # plain playback after the mirrored warm-up
-    [0, 1, 2, 1, 0, 3],                                    # warm-up outputs are not cached: 1 and 0 restart
+    [0, 1, 2, 1, 0, 3],                                    # frames 0.. are cached (the 16 mirrored warm-up outputs are not)
     list(range(0, 40)) + [39, 30, 24, 23, 40, 41],         # ring cache hits, then a miss beyond the ring
     [100, 101, 90, 150, 149, 166, 167, 200],               # seeks: within reach, out of reach, backwards
     [5, 25, 21, 22, 60, 44, 61],
@@ -104,3 +104,36 @@ def test_cxx_header_matches_model(trace_binary, requests):
                          text=True).stdout.splitlines()
     want = _model(requests)
     assert [" ".join(g.split()) for g in got] == [" ".join(w.split()) for w in want]
+
+
+# ---- the reference's own AviSynth filter, compiled unmodified ---------------------------------
+# oracle/Makefile builds avisynth_plugin/src/main.cc from /root/reference against a stand-in SDK
+# header (oracle/ref_avisynth/avisynth.h) and this repo's public include/JoshUpscale/core.h, with
+# a recording fake runtime (oracle/ref_avisynth/driver.cc).
+
+REF_MAIN = "/root/reference/avisynth_plugin/src/main.cc"
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "avisynth_trace")
+
+
+@pytest.fixture(scope="module")
+def reference_filter_binary():
+    if os.path.exists(REF_MAIN) and shutil.which("make") and shutil.which("g++"):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "_ref/avisynth_trace"], check=True,
+                       capture_output=True)
+    if not os.path.exists(REF_BIN):
+        pytest.skip("reference sources not available and oracle/_ref/avisynth_trace not prebuilt")
+    return REF_BIN
+
+
+@pytest.mark.parametrize("requests", SCRIPTS)
+def test_reference_avisynth_filter_matches_sequencer(reference_filter_binary, requests):
+    """Request by request, the reference's GetFrame must return the same frame and feed the same
+    source frames to processImage as the FrameSequencer policy (model, C++ header, Python twin)."""
+    got = subprocess.run([reference_filter_binary] + [str(n) for n in requests], check=True, capture_output=True,
+                         text=True).stdout.splitlines()
+    def head(line):  # "<n> -> <id> | <processed ...>" without the statistics the reference does not expose
+        first, processed = line.split("|")[:2]
+        return " ".join((first.strip() + " | " + processed.strip()).split())
+
+    assert [head(g + " |") for g in got] == [head(w) for w in _model(requests)]
+    assert [head(g + " |") for g in got] == [head(w) for w in _python(requests)]
