@@ -7,7 +7,9 @@
 //                         [H, W, 3] float32 / float16 engine input
 //   ref_tensor_to_image : engine output [H, W, 3] float32 -> BGRX u8 image
 #include <cstdint>
+#include <cstdio>
 #include <cstring>
+#include <exception>
 #include <vector>
 
 #include "JoshUpscale/core/cuda_convert.h"
@@ -20,6 +22,9 @@ int guarded(F &&f) {
 	try {
 		f();
 		return 0;
+	} catch (const std::exception &e) {
+		std::fprintf(stderr, "ref_convert: %s\n", e.what());
+		return 1;
 	} catch (...) {
 		return 1;
 	}
@@ -33,7 +38,9 @@ extern "C" __attribute__((visibility("default"))) int ref_image_to_tensor(const 
 		    static_cast<std::size_t>(width), static_cast<std::size_t>(height)};
 		const std::size_t n = static_cast<std::size_t>(width) * height * 3;
 		cuda::CudaStream stream;
-		cuda::CudaBuffer<std::uint8_t> internal(n);
+		// the staging buffer holds the 4-byte pixels (cuda_convert.cc.cu:365); the reference also
+		// requires width * height to be a multiple of 32 (:186)
+		cuda::CudaBuffer<std::uint8_t> internal(static_cast<std::size_t>(width) * height * 4);
 		GenericTensor from(img);
 		if (half_precision) {
 			cuda::CudaBuffer<__half> to(n);
@@ -56,7 +63,7 @@ extern "C" __attribute__((visibility("default"))) int ref_tensor_to_image(const 
 		    static_cast<std::size_t>(height)};
 		const std::size_t n = static_cast<std::size_t>(width) * height * 3;
 		cuda::CudaStream stream;
-		cuda::CudaBuffer<std::uint8_t> internal(n);
+		cuda::CudaBuffer<std::uint8_t> internal(static_cast<std::size_t>(width) * height * 4);
 		cuda::CudaBuffer<float> from(n);
 		cuda::cudaCheck(::cudaMemcpy(from.get(), host_in, n * sizeof(float), ::cudaMemcpyHostToDevice));
 		GenericTensor to(img);
