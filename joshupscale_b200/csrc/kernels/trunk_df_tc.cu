@@ -175,7 +175,10 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 	const unsigned int epoch = *reinterpret_cast<volatile unsigned int *>(p.sync_counter + 1);
 	const int n_waves = (p.total_tiles + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
 	// the 3x3 tile neighbourhood spans tile indices t +- (tiles_x + 1): that many waves ahead must be complete
-	const int wave_reach = (p.tiles_x + 1 + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+	// ... for THIS CTA: its furthest neighbour tile, index + tiles_x + 1, belongs to CTA
+	// (blockIdx.x + tiles_x + 1) % grid in wave k + (blockIdx.x + tiles_x + 1) / grid - so the first
+	// grid - tiles_x - 1 CTAs only need wave k itself, which was stored a full tile period earlier
+	const int wave_reach = (static_cast<int>(blockIdx.x) + p.tiles_x + 1) / static_cast<int>(gridDim.x);
 
 	if (warp == 0 || warp == kSecondProducerWarp) {
 		const int pme = warp == 0 ? 0 : 1;  // two producers, alternating tiles
