@@ -213,7 +213,7 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 						while (true) {
 							const bool ok = !mine || static_cast<int>(ld_relaxed_gpu(ctr) - target) >= 0;
 							if (__all_sync(0xffffffffu, ok)) break;
-							__nanosleep(32);
+							if (spins > 64) __nanosleep(32);  // tight relaxed polls first: the dependency is usually a few hundred ns away
 							if (++spins > (1u << 24)) {
 								if (p.error_flag) atomicExch(p.error_flag, 8);
 								__trap();
