@@ -812,7 +812,13 @@ void Engine::bindImages(int n, const ju_image *inputs, const ju_image *outputs) 
 			throw std::invalid_argument("GRAPHICS_RESOURCE images need a GL/D3D11 build (headless B200 build)");
 		}
 	}
-	JU_CUDA(cudaMemcpyAsync(m_IoDev.get(), io, sizeof(FrameIO) * m_Batch, cudaMemcpyHostToDevice, m_Stream));
+	// the device-side address table only changes when the caller's pointers do: host images always
+	// go through the same staging buffers, so their frames skip this copy
+	const std::size_t tableBytes = sizeof(FrameIO) * m_Batch;
+	if (m_IoShadow.size() != tableBytes || std::memcmp(m_IoShadow.data(), io, tableBytes) != 0) {
+		JU_CUDA(cudaMemcpyAsync(m_IoDev.get(), io, tableBytes, cudaMemcpyHostToDevice, m_Stream));
+		m_IoShadow.assign(reinterpret_cast<const unsigned char *>(io), reinterpret_cast<const unsigned char *>(io) + tableBytes);
+	}
 }
 
 void Engine::process(int n, const ju_image *inputs, const ju_image *outputs) {

@@ -110,6 +110,7 @@ private:
 
 	PinnedBuffer m_IoHost;
 	DeviceBuffer m_IoDev;
+	std::vector<unsigned char> m_IoShadow;  // last address table sent to the device
 	DeviceBuffer m_TcError;
 	DeviceBuffer m_Brightness;
 	DeviceBuffer m_TrunkWeights, m_TrunkBias, m_TrunkCounter, m_TrunkFlags;
