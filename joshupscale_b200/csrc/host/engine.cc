@@ -778,7 +778,11 @@ void Engine::bindImages(int n, const ju_image *inputs, const ju_image *outputs) 
 		if (in.location == JU_LOC_CPU) {
 			if (absStride(in.stride) < inRow) throw std::invalid_argument("input stride smaller than a row");
 			const auto *p = static_cast<const std::uint8_t *>(in.ptr);
-			if (in.stride >= 0) {
+			if (in.stride == static_cast<std::int64_t>(inRow)) {
+				JU_CUDA(cudaMemcpyAsync(inStage, p, inRow * H, cudaMemcpyHostToDevice, m_Stream));
+				f.in = inStage;
+				f.in_stride = static_cast<long long>(inRow);
+			} else if (in.stride >= 0) {
 				JU_CUDA(cudaMemcpy2DAsync(inStage, inRow, p, in.stride, inRow, H, cudaMemcpyHostToDevice, m_Stream));
 				f.in = inStage;
 				f.in_stride = static_cast<long long>(inRow);
@@ -851,7 +855,11 @@ void Engine::process(int n, const ju_image *inputs, const ju_image *outputs) {
 				const ju_image &out = outputs[s];
 				const std::uint8_t *stage = m_OutStage.as<std::uint8_t>() + s * 4 * H * outRow;
 				auto *p = static_cast<std::uint8_t *>(out.ptr);
-				if (out.stride >= 0) {
+				if (out.stride == static_cast<std::int64_t>(outRow)) {
+					// dense image: one linear copy
+					JU_CUDA(cudaMemcpyAsync(p + r.row0 * outRow, stage + r.row0 * outRow, rows * outRow,
+					    cudaMemcpyDeviceToHost, m_CopyStream));
+				} else if (out.stride >= 0) {
 					JU_CUDA(cudaMemcpy2DAsync(p + static_cast<std::int64_t>(r.row0) * out.stride, out.stride,
 					    stage + r.row0 * outRow, outRow, outRow, rows, cudaMemcpyDeviceToHost, m_CopyStream));
 				} else {
