@@ -455,12 +455,24 @@ void Engine::buildPlan(int parity, int variant) {
 		}
 		if (s.flowFilters.size() % 2) conv("flow/conv_1");
 	} else {
-		conv("flow/conv_1");
-		for (int i = 0; i < s.flowFilters[1]; ++i) {
-			std::string p = "flow/block_" + std::to_string(i + 1);
-			const __half *shortcut = x;
-			conv(p + "/conv_1");
-			conv(p + "/conv_2", shortcut);
+		const bool flowTrunk = m_ConvImpl == 1 && s.flowFilters[0] == 64 && s.flowFilters[1] > 0 &&
+		                       envInt("JU_FUSED_TRUNK", 1) != 0 && !m_Conv2Cta;
+		if (flowTrunk) {
+			// get_flow_resnet (models.py:257-331) is conv_1 + a ResBlock stack of the generator's shape:
+			// the same persistent trunk kernel runs it
+			const std::size_t bytes = static_cast<std::size_t>(B) * h * w * 64 * sizeof(__half);
+			__half *f0 = activation(bytes), *f1 = activation(bytes), *f2 = activation(bytes);
+			plan.push_back(convOp(layer("flow/conv_1"), x, xs, nullptr, f0, 64, h, w, false));
+			x = emitTrunk(plan, m_FlowTrunk, "flow", s.flowFilters[1], f0, f1, f2, 64, h, w, nullptr);
+			xs = 64;
+		} else {
+			conv("flow/conv_1");
+			for (int i = 0; i < s.flowFilters[1]; ++i) {
+				std::string p = "flow/block_" + std::to_string(i + 1);
+				const __half *shortcut = x;
+				conv(p + "/conv_1");
+				conv(p + "/conv_2", shortcut);
+			}
 		}
 	}
 	if (h != PH || w != PW) throw ModelException("flow net does not return to input resolution");
@@ -488,92 +500,21 @@ void Engine::buildPlan(int parity, int variant) {
 	const bool fusedTrunk = m_ConvImpl == 1 && s.genFilters == 64 && s.genBlocks > 0 && gs % 64 == 0 &&
 	                        envInt("JU_FUSED_TRUNK", 1) != 0 && !m_Conv2Cta;
 	if (fusedTrunk) {
-		// all 2 x genBlocks ResBlock convolutions in ONE persistent launch (trunk_tc.cu)
-		const int nLayers = 2 * s.genBlocks;
-		if (!m_TrunkWeights.get()) {
-			const std::size_t per = conv_tc_weight_bytes(3, 64, 64);
-			m_TrunkWeights = DeviceBuffer(per * nLayers);
-			m_TrunkBias = DeviceBuffer(sizeof(float) * 64 * nLayers);
-			m_TrunkCounter = DeviceBuffer(sizeof(unsigned int) * 2 * static_cast<std::size_t>(B));
-			m_TrunkFlags = DeviceBuffer(sizeof(unsigned int) * static_cast<std::size_t>(nLayers) * B * ((H + 15) / 16) * ((W + 7) / 8));
-			for (int l = 0; l < nLayers; ++l) {
-				ConvLayer *L = layer("generator/block_" + std::to_string(l / 2 + 1) + "/conv_" + std::to_string(l % 2 + 1));
-				if (!L->wTc.get() || L->cout != 64 || L->cinReal != 64 || L->ksize != 3) {
-					throw ModelException("unexpected ResBlock layer shape");
-				}
-				JU_CUDA(cudaMemcpy(m_TrunkWeights.as<char>() + per * l, L->wTc.get(), per, cudaMemcpyDeviceToDevice));
-				JU_CUDA(cudaMemcpy(m_TrunkBias.as<float>() + 64 * l, L->bias.get(), 64 * sizeof(float),
-				    cudaMemcpyDeviceToDevice));
-			}
-		}
-		ConvLayer *first = layer("generator/block_1/conv_1");
-		TrunkArgs ta{};
-		ta.buffers[0] = t0;
-		ta.buffers[1] = t1;
-		ta.buffers[2] = t2;
-		ta.cstride = gs;
-		ta.weights = m_TrunkWeights.get();
-		ta.bias = m_TrunkBias.as<float>();
-		ta.sync_counter = m_TrunkCounter.as<unsigned int>();
-		ta.flags = m_TrunkFlags.as<unsigned int>();
-		ta.batch = B;
-		ta.h = H;
-		ta.w = W;
-		ta.n_layers = nLayers;
-		ta.act = first->act;
-		ta.slope = first->slope;
-		// JU_TRUNK_SYNC: 1 = per-wave dataflow counters (trunk_df_tc.cu), 0 = grid barrier per layer
-		// (trunk_tc.cu), -1 (default) = dataflow.
-		// JU_TRUNK_SUBBATCH: with the dataflow trunk a large batch runs as consecutive launches of this
-		// many streams, each through ALL layers, so that the three trunk tensors of one launch stay
-		// resident in L2 (2 PSP streams = 100 MB of the 126 MB; one launch over 16 streams would
-		// stream ~800 MB per layer through HBM).  Default (-1): as many streams as fit 85 % of the
-		// L2; 0 = one launch for the whole batch.
-		const int syncMode = envInt("JU_TRUNK_SYNC", -1);
-		const bool dataflow = syncMode != 0;
-		const std::size_t perStream = static_cast<std::size_t>(H) * W * gs;
-		int chunk = dataflow ? envInt("JU_TRUNK_SUBBATCH", -1) : 0;
-		if (chunk < 0) {
-			int l2 = 0;
-			cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, m_Device);
-			const double budget = 0.85 * static_cast<double>(l2);
-			chunk = static_cast<int>(budget / (3.0 * perStream * sizeof(__half)));
-			if (chunk < 1) chunk = 1;
-		}
-		if (chunk <= 0 || chunk > B) chunk = B;
-		const std::size_t tilesPerStream = static_cast<std::size_t>((H + 15) / 16) * ((W + 7) / 8);
-		cur = trunk_output_buffer(nLayers) == 0 ? t0 : t2;
+		// all 2 x genBlocks ResBlock convolutions as persistent launches (trunk_df_tc.cu / trunk_tc.cu)
 		ConvLayer *ct1c = layer("generator/conv_trans_1");
-		const bool tailPerChunk = chunk < B && m_ConvImpl == 1 && ct1c->wTc.get() && gs % 64 == 0 &&
-		                          s.genFilters == 64 && envInt("JU_FUSED_TAIL", 1) != 0;
-		int *err = m_TcError.as<int>();
-		for (int b0 = 0; b0 < B; b0 += chunk) {
-			TrunkArgs sub = ta;
-			sub.batch = std::min(chunk, B - b0);
-			for (int i = 0; i < 3; ++i) sub.buffers[i] = static_cast<__half *>(ta.buffers[i]) + perStream * b0;
-			sub.sync_counter = ta.sync_counter + 2 * (b0 / chunk);
-			sub.flags = ta.flags + static_cast<std::size_t>(nLayers) * tilesPerStream * b0;
-			TrunkTcLaunch launch;
-			checkCuda(dataflow ? trunk_df_tc_prepare(sub, &launch) : trunk_tc_prepare(sub, &launch), "trunk_tc_prepare");
-			Op op;
-			op.name = "generator/block_*(persistent)";
-			op.tensorBound = true;
-			op.layers = b0 == 0 ? nLayers : 0;  // network layers are counted once, not once per sub-batch
-			op.flops = 2.0 * sub.batch * H * W * 9.0 * 64 * 64 * nLayers;
-			op.bytes = static_cast<double>(sub.batch) * H * W * 64 * 2.0 * (2.0 * nLayers + 0.5 * nLayers);
-			op.run = [launch, err, dataflow](cudaStream_t st) {
-				return dataflow ? trunk_df_tc_launch(launch, err, st) : trunk_tc_launch(launch, err, st);
-			};
-			plan.push_back(std::move(op));
-			++m_TcOps;
-			if (tailPerChunk) {
-				// The sub-batch is finished right away (tail kernel, output filter) and its completion
-				// is published as an event, so that process() can copy these streams' images to the
-				// host while the trunk of the next sub-batch is still running.
-				emitTail(plan, parity, cur, gs, b0, sub.batch);
-			}
-		}
-		if (tailPerChunk) {
+		const bool tailPerChunk = m_ConvImpl == 1 && ct1c->wTc.get() && gs % 64 == 0 && s.genFilters == 64 &&
+		                          envInt("JU_FUSED_TAIL", 1) != 0;
+		bool tailsEmitted = false;
+		cur = emitTrunk(plan, m_GenTrunk, "generator", s.genBlocks, t0, t1, t2, gs, H, W,
+		    [&](const __half *out, int b0, int nb, bool wholeBatch) {
+			    // With several sub-batches each one is finished right away (tail kernel, output filter)
+			    // and its completion is published as an event, so that process() can copy these streams'
+			    // images to the host while the trunk of the next sub-batch is still running.
+			    if (wholeBatch || !tailPerChunk) return;
+			    emitTail(plan, parity, out, gs, b0, nb);
+			    tailsEmitted = true;
+		    });
+		if (tailsEmitted) {
 			if (parity == 0) {
 				registerTensor("trunk", cur, nullptr, 1,
 				    {static_cast<std::uint64_t>(B), static_cast<std::uint64_t>(H), static_cast<std::uint64_t>(W),
@@ -621,6 +562,95 @@ void Engine::buildPlan(int parity, int variant) {
 	}
 	if (m_FilterOn) plan.push_back(filterOp(io, preGenNext, bright, 0, B));
 	plan.push_back(chunkDoneOp(0, B, 0, 4 * H));
+}
+
+// A stack of `nBlocks` ResBlocks (3x3 64->64 conv + BN + act, conv + BN + shortcut + act;
+// scripts/training/models.py:193-254) named <prefix>/block_<i>/conv_<j>, input in t0, as persistent
+// trunk launches.  Returns the buffer that holds the result; `afterChunk(result, b0, nb, whole)`
+// is called after the launch of every sub-batch.
+__half *Engine::emitTrunk(std::vector<Op> &plan, TrunkState &ts, const std::string &prefix, int nBlocks, __half *t0,
+    __half *t1, __half *t2, int cstride, int H, int W,
+    const std::function<void(const __half *, int, int, bool)> &afterChunk) {
+	const int B = m_Batch;
+	const int nLayers = 2 * nBlocks;
+	auto blockLayer = [&](int l) {
+		return m_LayerByName.at(prefix + "/block_" + std::to_string(l / 2 + 1) + "/conv_" + std::to_string(l % 2 + 1));
+	};
+	if (!ts.weights.get()) {
+		const std::size_t per = conv_tc_weight_bytes(3, 64, 64);
+		ts.weights = DeviceBuffer(per * nLayers);
+		ts.bias = DeviceBuffer(sizeof(float) * 64 * nLayers);
+		ts.counter = DeviceBuffer(sizeof(unsigned int) * 2 * static_cast<std::size_t>(B));
+		ts.flags = DeviceBuffer(sizeof(unsigned int) * static_cast<std::size_t>(nLayers) * B * ((H + 15) / 16) * ((W + 7) / 8));
+		for (int l = 0; l < nLayers; ++l) {
+			ConvLayer *L = blockLayer(l);
+			if (!L->wTc.get() || L->cout != 64 || L->cinReal != 64 || L->ksize != 3) {
+				throw ModelException("unexpected ResBlock layer shape");
+			}
+			JU_CUDA(cudaMemcpy(ts.weights.as<char>() + per * l, L->wTc.get(), per, cudaMemcpyDeviceToDevice));
+			JU_CUDA(cudaMemcpy(ts.bias.as<float>() + 64 * l, L->bias.get(), 64 * sizeof(float), cudaMemcpyDeviceToDevice));
+		}
+	}
+	ConvLayer *first = blockLayer(0);
+	TrunkArgs ta{};
+	ta.buffers[0] = t0;
+	ta.buffers[1] = t1;
+	ta.buffers[2] = t2;
+	ta.cstride = cstride;
+	ta.weights = ts.weights.get();
+	ta.bias = ts.bias.as<float>();
+	ta.sync_counter = ts.counter.as<unsigned int>();
+	ta.flags = ts.flags.as<unsigned int>();
+	ta.batch = B;
+	ta.h = H;
+	ta.w = W;
+	ta.n_layers = nLayers;
+	ta.act = first->act;
+	ta.slope = first->slope;
+	// JU_TRUNK_SYNC: 0 = grid barrier per layer (trunk_tc.cu), otherwise (default) per-wave dataflow
+	// counters (trunk_df_tc.cu).
+	// JU_TRUNK_SUBBATCH: with the dataflow trunk a large batch runs as consecutive launches of this
+	// many streams, each through ALL layers, so that the three trunk tensors of one launch stay
+	// resident in L2 (2 PSP streams = 100 MB of the 126 MB; one launch over 16 streams would
+	// stream ~800 MB per layer through HBM).  Default (-1): as many streams as fit 85 % of the
+	// L2; 0 = one launch for the whole batch.
+	const int syncMode = envInt("JU_TRUNK_SYNC", -1);
+	const bool dataflow = syncMode != 0;
+	const std::size_t perStream = static_cast<std::size_t>(H) * W * cstride;
+	int chunk = dataflow ? envInt("JU_TRUNK_SUBBATCH", -1) : 0;
+	if (chunk < 0) {
+		int l2 = 0;
+		cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, m_Device);
+		const double budget = 0.85 * static_cast<double>(l2);
+		chunk = static_cast<int>(budget / (3.0 * perStream * sizeof(__half)));
+		if (chunk < 1) chunk = 1;
+	}
+	if (chunk <= 0 || chunk > B) chunk = B;
+	const std::size_t tilesPerStream = static_cast<std::size_t>((H + 15) / 16) * ((W + 7) / 8);
+	__half *result = trunk_output_buffer(nLayers) == 0 ? t0 : t2;
+	int *err = m_TcError.as<int>();
+	for (int b0 = 0; b0 < B; b0 += chunk) {
+		TrunkArgs sub = ta;
+		sub.batch = std::min(chunk, B - b0);
+		for (int i = 0; i < 3; ++i) sub.buffers[i] = static_cast<__half *>(ta.buffers[i]) + perStream * b0;
+		sub.sync_counter = ta.sync_counter + 2 * (b0 / chunk);
+		sub.flags = ta.flags + static_cast<std::size_t>(nLayers) * tilesPerStream * b0;
+		TrunkTcLaunch launch;
+		checkCuda(dataflow ? trunk_df_tc_prepare(sub, &launch) : trunk_tc_prepare(sub, &launch), "trunk_tc_prepare");
+		Op op;
+		op.name = prefix + "/block_*(persistent)";
+		op.tensorBound = true;
+		op.layers = b0 == 0 ? nLayers : 0;  // network layers are counted once, not once per sub-batch
+		op.flops = 2.0 * sub.batch * H * W * 9.0 * 64 * 64 * nLayers;
+		op.bytes = static_cast<double>(sub.batch) * H * W * 64 * 2.0 * (2.0 * nLayers + 0.5 * nLayers);
+		op.run = [launch, err, dataflow](cudaStream_t st) {
+			return dataflow ? trunk_df_tc_launch(launch, err, st) : trunk_tc_launch(launch, err, st);
+		};
+		plan.push_back(std::move(op));
+		++m_TcOps;
+		if (afterChunk) afterChunk(result, b0, sub.batch, chunk >= B);
+	}
+	return result;
 }
 
 // Fused tail (+ output filter) for streams [b0, b0 + nb), followed by the event that tells

@@ -56,6 +56,11 @@ struct NamedTensor {
 	bool writable = false;
 };
 
+// packed weights / bias and synchronisation words of one persistent ResBlock stack
+struct TrunkState {
+	DeviceBuffer weights, bias, counter, flags;
+};
+
 class Engine {
 public:
 	Engine(const ModelFile &model, int device, int batch);
@@ -88,6 +93,9 @@ private:
 	void destroyGraphsAndEvents();
 	ConvLayer *addConv(const std::string &name, const FoldedConv &f, int act, float slope, bool shuffle2);
 	Op filterOp(const FrameIO *io, __half *preGenNext, const float *bright, int b0, int nb);
+	__half *emitTrunk(std::vector<Op> &plan, TrunkState &ts, const std::string &prefix, int nBlocks, __half *t0,
+	    __half *t1, __half *t2, int cstride, int H, int W,
+	    const std::function<void(const __half *, int, int, bool)> &afterChunk);
 	void emitTail(std::vector<Op> &plan, int parity, const __half *trunkOut, int gs, int b0, int nb);
 	Op chunkDoneOp(int b0, int nb, int row0, int row1);
 	Op convOp(ConvLayer *layer, const __half *in, int cinStride, const __half *residual, void *out,
@@ -113,7 +121,7 @@ private:
 	std::vector<unsigned char> m_IoShadow;  // last address table sent to the device
 	DeviceBuffer m_TcError;
 	DeviceBuffer m_Brightness;
-	DeviceBuffer m_TrunkWeights, m_TrunkBias, m_TrunkCounter, m_TrunkFlags;
+	TrunkState m_GenTrunk, m_FlowTrunk;
 	int m_TcOps = 0;
 	DeviceBuffer m_InStage, m_OutStage;
 	std::vector<ju_image> m_LastOutputs;

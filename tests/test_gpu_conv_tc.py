@@ -266,3 +266,37 @@ def test_execution_switches_do_not_change_the_bytes(tmp_path, env):
         np.testing.assert_array_equal(want_s[t], want_b[t][0])
         for s in range(3):
             np.testing.assert_array_equal(got_b[t][s], want_b[t][s])
+
+
+def test_flow_resnet_runs_on_the_persistent_trunk_bit_identically(tmp_path):
+    """get_flow_resnet is conv_1 + ResBlocks of the generator's shape: the engine runs them with the
+    persistent trunk kernel.  Same bytes as one conv launch per layer, also with sub-batches."""
+    from joshupscale_b200 import config as jcfg
+    cfg = jcfg.ModelConfig(frame_height=136, frame_width=240, gen_blocks=2, flow_arch="resnet",
+                           flow_resnet_blocks=4, flow_pad_factor=0)
+    cfg2, _, path = make_model(tmp_path, cfg)
+    clips = [synthetic.frames(cfg.frame_height, cfg.frame_width, 3, stream_id=s) for s in range(3)]
+
+    def run():
+        with jrt.Runtime(path, 0, 3) as rt:
+            names = [o["name"] for o in rt.profile_ops(1)]
+            rt.reset_state()
+            return names, [[o.copy() for o in rt.process_batch([c[t] for c in clips])] for t in range(3)]
+
+    names, want = run()
+    assert any(n.startswith("flow/block_*(persistent)") for n in names), names
+    os.environ["JU_FUSED_TRUNK"] = "0"
+    try:
+        names0, got = run()
+    finally:
+        os.environ.pop("JU_FUSED_TRUNK", None)
+    assert not any("persistent" in n for n in names0)
+    os.environ["JU_TRUNK_SUBBATCH"] = "1"
+    try:
+        _, got1 = run()
+    finally:
+        os.environ.pop("JU_TRUNK_SUBBATCH", None)
+    for t in range(3):
+        for s in range(3):
+            np.testing.assert_array_equal(got[t][s], want[t][s])
+            np.testing.assert_array_equal(got1[t][s], want[t][s])
