@@ -154,6 +154,8 @@ def preset(name: str) -> ModelConfig:
         # PS2 size inferred from obs_plugin/data/mask.png (1920x1440)
         "ps2_quality": ModelConfig(frame_height=360, frame_width=480),
         "ps2_fast": ModelConfig(frame_height=360, frame_width=480, gen_blocks=8),
+        # the alternative flow architecture (get_flow_resnet defaults, models.py:257-263) at PSP size
+        "psp_resnet": ModelConfig(flow_arch="resnet", flow_pad_factor=0),
         # small shapes for CPU-side parity tests (exercise asymmetric padding)
         "tiny": ModelConfig(frame_height=21, frame_width=27, gen_blocks=2,
                             flow_filters=(8, 16, 16, 32, 16, 16, 8)),
