@@ -5,6 +5,7 @@ import os
 import shutil
 import subprocess
 
+import numpy as np
 import pytest
 
 from joshupscale_b200 import sequencer as js
@@ -137,3 +138,43 @@ def test_reference_avisynth_filter_matches_sequencer(reference_filter_binary, re
 
     assert [head(g + " |") for g in got] == [head(w) for w in _model(requests)]
     assert [head(g + " |") for g in got] == [head(w) for w in _python(requests)]
+
+
+def _random_scripts(count=24, seed=2024):
+    """Playback with scrubbing: mostly +1, some small steps back / forward, occasional far seeks."""
+    rng = np.random.default_rng(seed)
+    scripts = []
+    for _ in range(count):
+        n, out = int(rng.integers(0, 50)), []
+        for _ in range(int(rng.integers(20, 70))):
+            r = rng.random()
+            if r < 0.55:
+                n += 1
+            elif r < 0.75:
+                n -= int(rng.integers(1, 6))
+            elif r < 0.88:
+                n += int(rng.integers(2, 20))
+            elif r < 0.95:
+                n -= int(rng.integers(10, 40))
+            else:
+                n += int(rng.integers(20, 200))
+            n = max(n, 0)
+            out.append(n)
+        scripts.append(out)
+    return scripts
+
+
+def test_random_scrubbing_reference_header_and_twin_agree(reference_filter_binary, trace_binary):
+    """Randomised request sequences: the reference's compiled AviSynth filter, the C++ header and
+    the Python twin must return the same frames and issue the same processImage calls."""
+    def head(line):
+        first, processed = line.split("|")[:2]
+        return " ".join((first.strip() + " | " + processed.strip()).split())
+
+    for requests in _random_scripts():
+        args = [str(n) for n in requests]
+        ref = subprocess.run([reference_filter_binary] + args, check=True, capture_output=True, text=True)
+        hdr = subprocess.run([trace_binary] + args, check=True, capture_output=True, text=True)
+        ref_lines = [head(g + " |") for g in ref.stdout.splitlines()]
+        assert ref_lines == [head(g) for g in hdr.stdout.splitlines()], requests
+        assert ref_lines == [head(g) for g in _python(requests)], requests
