@@ -6,6 +6,24 @@
 // Every declaration cites the reference line it replaces.  The engine behind
 // createRuntime() is hand-written sm_100a CUDA instead of a TensorRT engine;
 // `modelPath` therefore names a `.jup` weight container, not a `.trt` file.
+//
+// Typical caller (what both plugins do, avisynth_plugin/src/main.cc:57-68, 125-148):
+//
+//     std::unique_ptr<core::Runtime> rt;
+//     try {
+//         rt.reset(core::createRuntime(/*deviceId=*/0, "model_psp.jup"));
+//     } catch (...) {
+//         report(core::getExceptionString());        // must be called inside the catch block
+//     }
+//     // frames must match the model: rt->getInputWidth() x rt->getInputHeight() in,
+//     // 4x that out; BGRX, any signed byte stride, host or device memory
+//     core::Image in{src, core::DataLocation::CPU, srcPitch, w, h};
+//     core::Image out{dst, core::DataLocation::CPU, dstPitch, 4 * w, 4 * h};
+//     rt->processImage(in, out);                      // synchronous; advances the recurrent state
+//
+// Behaviour that differs from the reference build is listed in INTEGRATION.md section 1
+// (model file format, graphics-resource images, size mismatch reporting).  The same engine is
+// reachable through a plain C ABI, include/joshupscale_c.h, for FFI callers.
 #pragma once
 
 #include <cstddef>
@@ -82,6 +100,12 @@ protected:
 	std::size_t m_OutputHeight = 0;
 };
 
+// Creates a runtime on CUDA device `deviceId` from the weight container at `modelPath`:
+// loads and folds the weights, allocates the activation / state buffers for one stream and
+// captures the frame's CUDA graphs, so the first processImage() call is as fast as any other.
+// Throws (std::invalid_argument for a bad device index, ju::ModelException for an unreadable or
+// unsupported model - e.g. a TensorRT `.trt` engine -, ju::CudaException for CUDA failures).
+// Several runtimes may coexist, also on the same device; each owns its stream and state.
 // Caller owns the returned pointer (delete through the virtual destructor).
 JOSHUPSCALE_EXPORT Runtime *createRuntime(int deviceId, const std::filesystem::path &modelPath);
 
