@@ -409,3 +409,23 @@ def test_engine_matches_vectors_from_the_reference_built_graph(tmp_path, name):
     for t in range(frames.shape[0]):
         m, _, psnr = u8_stats(got[t, ..., :3], gold[f"{name}/output"][t])
         assert m <= MAX_ABS_FP32 and psnr >= MIN_PSNR_DB, (name, t, m, psnr)
+
+
+def test_alternating_host_and_device_images_on_one_runtime(tmp_path):
+    """One runtime, calls alternating between host and device-resident images: the two frame-plan
+    variants (banded tail with overlapped copies / single pass) share the recurrent state."""
+    cfg, _, path = make_model(tmp_path, "psp_fast")
+    h, w = cfg.frame_height, cfg.frame_width
+    frames = synthetic.frames(h, w, 5)
+    want = _run_gpu(path, frames)
+    d_in, d_out = jk.DeviceArray((h, w, 4), np.uint8), jk.DeviceArray((4 * h, 4 * w, 4), np.uint8)
+    with jrt.Runtime(path, 0, 1) as rt:
+        for t, f in enumerate(frames):
+            if t % 2:
+                d_in.upload(np.ascontiguousarray(f))
+                rt.process_images([jrt.JuImage(d_in.ptr, jrt.LOC_CUDA, w * 4, w, h)],
+                                  [jrt.JuImage(d_out.ptr, jrt.LOC_CUDA, w * 16, 4 * w, 4 * h)])
+                got = d_out.download()
+            else:
+                got = rt.process(f)
+            np.testing.assert_array_equal(got, want[t])
