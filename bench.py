@@ -379,7 +379,8 @@ def run_ours(args):
             "traffic_note": "dram bytes per launch (all layers, %d stream(s)) from ncu --set full of this kernel inside "
                             "bench.py (profiles/ncu_traffic.json); algorithmic bytes per launch = %d"
                             % (chunk if persistent else streams, int(bytes_per_layer * layers / max(trunk_launches, 1))),
-            "kernel": ("trunk_df_tc_kernel: all ResBlock conv3x3 64->64 layers of %d stream(s) in one persistent launch" % chunk
+            "kernel": ("trunk_df_tc_kernel: generator conv_1 + all ResBlock conv3x3 64->64 layers of %d stream(s) in one "
+                       "persistent launch" % chunk
                        if persistent else "conv_tc_kernel<3,1>: ResBlock conv3x3 64->64 (generator/block_*/conv_*)"),
             "layers_per_step": layers, "kernel_launches_per_step": trunk_launches, "usec_per_layer": mean_usec,
             "usec_per_launch": res_usec / trunk_launches,

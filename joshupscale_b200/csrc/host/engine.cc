@@ -463,7 +463,7 @@ void Engine::buildPlan(int parity, int variant) {
 			const std::size_t bytes = static_cast<std::size_t>(B) * h * w * 64 * sizeof(__half);
 			__half *f0 = activation(bytes), *f1 = activation(bytes), *f2 = activation(bytes);
 			plan.push_back(convOp(layer("flow/conv_1"), x, xs, nullptr, f0, 64, h, w, false));
-			x = emitTrunk(plan, m_FlowTrunk, "flow", s.flowFilters[1], f0, f1, f2, 64, h, w, nullptr);
+			x = emitTrunk(plan, m_FlowTrunk, "flow", s.flowFilters[1], f0, f1, f2, 64, h, w, nullptr, nullptr, nullptr);
 			xs = 64;
 		} else {
 			conv("flow/conv_1");
@@ -495,18 +495,22 @@ void Engine::buildPlan(int parity, int variant) {
 	// ---- generator -----------------------------------------------------
 	const int gs = pad64(std::max(s.genFilters, 51));
 	__half *t0 = m_Trunk[0].as<__half>(), *t1 = m_Trunk[1].as<__half>(), *t2 = m_Trunk[2].as<__half>();
-	plan.push_back(convOp(layer("generator/conv_1"), m_GenIn.as<__half>(), 64, nullptr, t0, gs, H, W, false));
 	__half *cur = t0, *tmp = t1, *nxt = t2;
 	const bool fusedTrunk = m_ConvImpl == 1 && s.genFilters == 64 && s.genBlocks > 0 && gs % 64 == 0 &&
 	                        envInt("JU_FUSED_TRUNK", 1) != 0 && !m_Conv2Cta;
+	// conv_1 runs as layer 0 of the dataflow trunk when it can (emitTrunk decides the same way)
+	ConvLayer *gc1 = layer("generator/conv_1");
+	const bool conv1InTrunk = fusedTrunk && envInt("JU_TRUNK_SYNC", -1) != 0 && envInt("JU_TRUNK_LEAD", 1) != 0 &&
+	                          gc1->wTc.get() && gc1->cout == 64 && gc1->ksize == 3 && gs == 64;
+	if (!conv1InTrunk) plan.push_back(convOp(gc1, m_GenIn.as<__half>(), 64, nullptr, t0, gs, H, W, false));
 	if (fusedTrunk) {
 		// all 2 x genBlocks ResBlock convolutions as persistent launches (trunk_df_tc.cu / trunk_tc.cu)
 		ConvLayer *ct1c = layer("generator/conv_trans_1");
 		const bool tailPerChunk = m_ConvImpl == 1 && ct1c->wTc.get() && gs % 64 == 0 && s.genFilters == 64 &&
 		                          envInt("JU_FUSED_TAIL", 1) != 0;
 		bool tailsEmitted = false;
-		cur = emitTrunk(plan, m_GenTrunk, "generator", s.genBlocks, t0, t1, t2, gs, H, W,
-		    [&](const __half *out, int b0, int nb, bool wholeBatch) {
+		cur = emitTrunk(plan, m_GenTrunk, "generator", s.genBlocks, t0, t1, t2, gs, H, W, conv1InTrunk ? gc1 : nullptr,
+		    m_GenIn.as<__half>(), [&](const __half *out, int b0, int nb, bool wholeBatch) {
 			    // With several sub-batches each one is finished right away (tail kernel, output filter)
 			    // and its completion is published as an event, so that process() can copy these streams'
 			    // images to the host while the trunk of the next sub-batch is still running.
@@ -570,10 +574,22 @@ void Engine::buildPlan(int parity, int variant) {
 // is called after the launch of every sub-batch.
 __half *Engine::emitTrunk(std::vector<Op> &plan, TrunkState &ts, const std::string &prefix, int nBlocks, __half *t0,
     __half *t1, __half *t2, int cstride, int H, int W,
-    const std::function<void(const __half *, int, int, bool)> &afterChunk) {
+    ConvLayer *lead, const __half *leadIn, const std::function<void(const __half *, int, int, bool)> &afterChunk) {
 	const int B = m_Batch;
-	const int nLayers = 2 * nBlocks;
+	const int nBlockLayers = 2 * nBlocks;
+	const int syncMode = envInt("JU_TRUNK_SYNC", -1);
+	const bool dataflow = syncMode != 0;
+	// optional plain conv in front of the ResBlocks (the generator's conv_1): same 3x3 64->64 shape
+	// once its 51 input channels are padded, so it becomes layer 0 of the dataflow trunk
+	if (lead && !(dataflow && envInt("JU_TRUNK_LEAD", 1) != 0 && lead->wTc.get() && lead->cout == 64 && lead->ksize == 3 &&
+	                 lead->cinReal <= 64 && cstride == 64)) {
+		lead = nullptr;
+	}
+	const int nLead = lead ? 1 : 0;
+	const int nLayers = nBlockLayers + nLead;
 	auto blockLayer = [&](int l) {
+		if (lead && l == 0) return lead;
+		l -= nLead;
 		return m_LayerByName.at(prefix + "/block_" + std::to_string(l / 2 + 1) + "/conv_" + std::to_string(l % 2 + 1));
 	};
 	if (!ts.weights.get()) {
@@ -584,14 +600,17 @@ __half *Engine::emitTrunk(std::vector<Op> &plan, TrunkState &ts, const std::stri
 		ts.flags = DeviceBuffer(sizeof(unsigned int) * static_cast<std::size_t>(nLayers) * B * ((H + 15) / 16) * ((W + 7) / 8));
 		for (int l = 0; l < nLayers; ++l) {
 			ConvLayer *L = blockLayer(l);
-			if (!L->wTc.get() || L->cout != 64 || L->cinReal != 64 || L->ksize != 3) {
+			if (!L->wTc.get() || L->cout != 64 || (L != lead && L->cinReal != 64) || L->ksize != 3) {
 				throw ModelException("unexpected ResBlock layer shape");
 			}
 			JU_CUDA(cudaMemcpy(ts.weights.as<char>() + per * l, L->wTc.get(), per, cudaMemcpyDeviceToDevice));
 			JU_CUDA(cudaMemcpy(ts.bias.as<float>() + 64 * l, L->bias.get(), 64 * sizeof(float), cudaMemcpyDeviceToDevice));
 		}
 	}
-	ConvLayer *first = blockLayer(0);
+	ConvLayer *first = blockLayer(nLead);
+	if (lead && (lead->act != first->act || lead->slope != first->slope)) {
+		throw ModelException("lead convolution and ResBlocks use different activations");
+	}
 	TrunkArgs ta{};
 	ta.buffers[0] = t0;
 	ta.buffers[1] = t1;
@@ -607,6 +626,7 @@ __half *Engine::emitTrunk(std::vector<Op> &plan, TrunkState &ts, const std::stri
 	ta.n_layers = nLayers;
 	ta.act = first->act;
 	ta.slope = first->slope;
+	ta.lead_in = lead ? leadIn : nullptr;
 	// JU_TRUNK_SYNC: 0 = grid barrier per layer (trunk_tc.cu), otherwise (default) per-wave dataflow
 	// counters (trunk_df_tc.cu).
 	// JU_TRUNK_SUBBATCH: with the dataflow trunk a large batch runs as consecutive launches of this
@@ -614,8 +634,6 @@ __half *Engine::emitTrunk(std::vector<Op> &plan, TrunkState &ts, const std::stri
 	// resident in L2 (2 PSP streams = 100 MB of the 126 MB; one launch over 16 streams would
 	// stream ~800 MB per layer through HBM).  Default (-1): as many streams as fit 85 % of the
 	// L2; 0 = one launch for the whole batch.
-	const int syncMode = envInt("JU_TRUNK_SYNC", -1);
-	const bool dataflow = syncMode != 0;
 	const std::size_t perStream = static_cast<std::size_t>(H) * W * cstride;
 	int chunk = dataflow ? envInt("JU_TRUNK_SUBBATCH", -1) : 0;
 	if (chunk < 0) {
@@ -627,7 +645,8 @@ __half *Engine::emitTrunk(std::vector<Op> &plan, TrunkState &ts, const std::stri
 	}
 	if (chunk <= 0 || chunk > B) chunk = B;
 	const std::size_t tilesPerStream = static_cast<std::size_t>((H + 15) / 16) * ((W + 7) / 8);
-	__half *result = trunk_output_buffer(nLayers) == 0 ? t0 : t2;
+	__half *result = trunk_output_buffer(nBlockLayers) == 0 ? t0 : t2;
+	const double leadFlops = lead ? 2.0 * H * W * 9.0 * lead->cinReal * 64 : 0.0;
 	int *err = m_TcError.as<int>();
 	for (int b0 = 0; b0 < B; b0 += chunk) {
 		TrunkArgs sub = ta;
@@ -635,13 +654,14 @@ __half *Engine::emitTrunk(std::vector<Op> &plan, TrunkState &ts, const std::stri
 		for (int i = 0; i < 3; ++i) sub.buffers[i] = static_cast<__half *>(ta.buffers[i]) + perStream * b0;
 		sub.sync_counter = ta.sync_counter + 2 * (b0 / chunk);
 		sub.flags = ta.flags + static_cast<std::size_t>(nLayers) * tilesPerStream * b0;
+		if (lead) sub.lead_in = leadIn + perStream * b0;
 		TrunkTcLaunch launch;
 		checkCuda(dataflow ? trunk_df_tc_prepare(sub, &launch) : trunk_tc_prepare(sub, &launch), "trunk_tc_prepare");
 		Op op;
 		op.name = prefix + "/block_*(persistent)";
 		op.tensorBound = true;
 		op.layers = b0 == 0 ? nLayers : 0;  // network layers are counted once, not once per sub-batch
-		op.flops = 2.0 * sub.batch * H * W * 9.0 * 64 * 64 * nLayers;
+		op.flops = 2.0 * sub.batch * H * W * 9.0 * 64 * 64 * nBlockLayers + sub.batch * leadFlops;
 		op.bytes = static_cast<double>(sub.batch) * H * W * 64 * 2.0 * (2.0 * nLayers + 0.5 * nLayers);
 		op.run = [launch, err, dataflow](cudaStream_t st) {
 			return dataflow ? trunk_df_tc_launch(launch, err, st) : trunk_tc_launch(launch, err, st);

@@ -94,7 +94,7 @@ private:
 	ConvLayer *addConv(const std::string &name, const FoldedConv &f, int act, float slope, bool shuffle2);
 	Op filterOp(const FrameIO *io, __half *preGenNext, const float *bright, int b0, int nb);
 	__half *emitTrunk(std::vector<Op> &plan, TrunkState &ts, const std::string &prefix, int nBlocks, __half *t0,
-	    __half *t1, __half *t2, int cstride, int H, int W,
+	    __half *t1, __half *t2, int cstride, int H, int W, ConvLayer *lead, const __half *leadIn,
 	    const std::function<void(const __half *, int, int, bool)> &afterChunk);
 	void emitTail(std::vector<Op> &plan, int parity, const __half *trunkOut, int gs, int b0, int nb);
 	Op chunkDoneOp(int b0, int nb, int row0, int row1);

@@ -135,12 +135,16 @@ struct TrunkArgs {
 	unsigned int *sync_counter;  // two zero-initialised device words per engine (counter, epoch)
 	unsigned int *flags;         // dataflow version: zero-initialised [n_layers][waves] counters (>= n_layers * tiles words)
 	int batch, h, w;
-	int n_layers;            // 2 x ResBlocks
+	int n_layers;            // 2 x ResBlocks (+ 1 if lead_in is set)
 	int act;
 	float slope;
+	// dataflow version only: an extra plain 3x3 64->64 conv + act in front of the ResBlocks (the
+	// generator's conv_1), reading this tensor [batch, h, w, cstride] and writing T0; its weights
+	// and bias come first in `weights` / `bias`
+	const void *lead_in;
 };
 struct TrunkTcLaunch {
-	alignas(64) unsigned char maps[7 * 128];
+	alignas(64) unsigned char maps[8 * 128];
 	alignas(8) unsigned char params[128];
 	int grid;
 	unsigned int smem_bytes;

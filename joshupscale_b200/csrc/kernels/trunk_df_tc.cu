@@ -76,10 +76,11 @@ struct TrunkParams {
 	int *error_flag;
 	const __half *buffers[3];     // T0, T1, T2 (residual rows are read straight from global memory)
 	int cstride;
+	int lead;  // layer 0 is a plain conv reading maps.in[3] and writing T0; ResBlock layers follow
 };
 
 struct TrunkMaps {
-	CUtensorMap in[3];    // halo boxes (64 ch, 10, 18, 1) over T0, T1, T2
+	CUtensorMap in[4];    // halo boxes (64 ch, 10, 18, 1) over T0, T1, T2 and the lead layer's input
 	CUtensorMap tile[3];  // pixel tiles (64 ch, 8, 16, 1) over T0, T1, T2: output stores
 	CUtensorMap w;        // weights of all layers: rows [layer][tap][cout], 64 ch each
 };
@@ -167,9 +168,23 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 		b = rest / p.tiles_y;
 	};
 	// layer l = 2*block + conv: buffers (see header)
-	auto layer_in = [](int l) { return (l & 1) ? 1 : (((l >> 1) & 1) ? 2 : 0); };
-	auto layer_res = [](int l) { return (l & 1) ? (((l >> 1) & 1) ? 2 : 0) : -1; };
-	auto layer_out = [](int l) { return (l & 1) ? (((l >> 1) & 1) ? 0 : 2) : 1; };
+	// with a lead layer everything shifts by one: lead reads buffer 3 and writes T0
+	const int lead = p.lead;
+	auto layer_in = [lead](int l) {
+		if (lead && l == 0) return 3;
+		l -= lead;
+		return (l & 1) ? 1 : (((l >> 1) & 1) ? 2 : 0);
+	};
+	auto layer_res = [lead](int l) {
+		if (lead && l == 0) return -1;
+		l -= lead;
+		return (l & 1) ? (((l >> 1) & 1) ? 2 : 0) : -1;
+	};
+	auto layer_out = [lead](int l) {
+		if (lead && l == 0) return 0;
+		l -= lead;
+		return (l & 1) ? (((l >> 1) & 1) ? 0 : 2) : 1;
+	};
 
 	// launch epoch: identical for every CTA of this launch (advanced by the last CTA to finish)
 	const unsigned int epoch = *reinterpret_cast<volatile unsigned int *>(p.sync_counter + 1);
@@ -355,7 +370,7 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 			float bias_reg[32];
 #pragma unroll
 			for (int c = 0; c < 32; ++c) bias_reg[c] = __ldg(p.bias + l * 64 + half * 32 + c);
-			const bool has_res = (l & 1) != 0;
+			const bool has_res = layer_res(l) >= 0;
 			const __half *res_buf = has_res ? p.buffers[layer_res(l)] : nullptr;
 			for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
 				const int as = it % kAccStages;
@@ -468,9 +483,10 @@ constexpr uint32_t kFixed = 1024u + 768u + kBBytes + kStoreWarps * kEpiTile;  //
 cudaError_t trunk_df_tc_prepare(const TrunkArgs &a, TrunkTcLaunch *out) {
 	EncodeTiledFn encode = encodeTiledDF();
 	if (!encode) return cudaErrorNotSupported;
-	if (a.cstride % 64 || a.n_layers < 1 || (a.n_layers & 1)) return cudaErrorInvalidValue;
+	const int lead = a.lead_in ? 1 : 0;
+	if (a.cstride % 64 || a.n_layers - lead < 2 || ((a.n_layers - lead) & 1)) return cudaErrorInvalidValue;
 	static_assert(sizeof(TrunkParams) <= sizeof(out->params), "TrunkTcLaunch::params too small");
-	static_assert(sizeof(TrunkMaps) == sizeof(out->maps), "TrunkTcLaunch::maps size mismatch");
+	static_assert(sizeof(TrunkMaps) <= sizeof(out->maps), "TrunkTcLaunch::maps too small");
 	TrunkParams p{};
 	p.batch = a.batch;
 	p.h = a.h;
@@ -488,6 +504,7 @@ cudaError_t trunk_df_tc_prepare(const TrunkArgs &a, TrunkTcLaunch *out) {
 	if (!a.flags) return cudaErrorInvalidValue;
 	for (int i = 0; i < 3; ++i) p.buffers[i] = static_cast<const __half *>(a.buffers[i]);
 	p.cstride = a.cstride;
+	p.lead = lead;
 	int stages = static_cast<int>((kSmemLimit - kFixed) / kARegion);
 	if (stages > kMaxStages) stages = kMaxStages;
 	// The two producer / issuer pairs take tiles alternately.  With an EVEN stage count each pair
@@ -513,6 +530,14 @@ cudaError_t trunk_df_tc_prepare(const TrunkArgs &a, TrunkTcLaunch *out) {
 		        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS ||
 		    encode(&maps.tile[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, a.buffers[i], dims, strides, tbox, estr,
 		        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+		        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+			return cudaErrorInvalidValue;
+		}
+	}
+	if (lead) {
+		cuuint32_t hbox[4] = {64, 10, 18, 1};
+		if (encode(&maps.in[3], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(a.lead_in), dims, strides, hbox,
+		        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
 		        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
 			return cudaErrorInvalidValue;
 		}

@@ -356,9 +356,9 @@ constexpr uint32_t kFixed = 1024u + 512u + kBBytes + 4u * kEpiTile;
 cudaError_t trunk_tc_prepare(const TrunkArgs &a, TrunkTcLaunch *out) {
 	EncodeTiledFn encode = encodeTiledT();
 	if (!encode) return cudaErrorNotSupported;
-	if (a.cstride % 64 || a.n_layers < 1 || (a.n_layers & 1)) return cudaErrorInvalidValue;
+	if (a.cstride % 64 || a.n_layers < 1 || (a.n_layers & 1) || a.lead_in) return cudaErrorInvalidValue;
 	static_assert(sizeof(TrunkParams) <= sizeof(out->params), "TrunkTcLaunch::params too small");
-	static_assert(sizeof(TrunkMaps) == sizeof(out->maps), "TrunkTcLaunch::maps size mismatch");
+	static_assert(sizeof(TrunkMaps) <= sizeof(out->maps), "TrunkTcLaunch::maps too small");
 	TrunkParams p{};
 	p.batch = a.batch;
 	p.h = a.h;
