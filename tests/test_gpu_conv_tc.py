@@ -232,6 +232,7 @@ def test_dataflow_trunk_race_stress(tmp_path):
     {"JU_TRUNK_SUBBATCH": "0"},
     {"JU_TRUNK_SUBBATCH": "1"},
     {"JU_TAIL_BANDS": "1"},
+    {"JU_TRUNK_LEAD": "0"},
     {"JU_TAIL_BANDS": "5", "JU_NO_GRAPH": "1"},
 ])
 def test_execution_switches_do_not_change_the_bytes(tmp_path, env):
