@@ -33,6 +33,11 @@
 
 #include "JoshUpscale/core/export.h"
 
+#ifdef _WIN32
+struct ID3D11Texture2D;
+struct ID3D11Device;
+#endif
+
 namespace JoshUpscale {
 namespace core {
 
@@ -62,9 +67,10 @@ struct Image {
 };
 
 // ---- graphics interop (reference core.h:40-62) ---------------------------
-// Declared for source compatibility.  This headless build has no GL/D3D11
-// context: getGLImage() throws std::runtime_error and getGLDeviceIndex()
-// returns -1 unless the library is compiled with JOSHUPSCALE_WITH_GL.
+// getGLImage() registers a GL_TEXTURE_2D of the calling thread's current GL context with CUDA
+// (the GL entry points are resolved from the process's libGL at call time, the library itself
+// links no GL); the returned image (location GRAPHICS_RESOURCE) can be passed to processImage().
+// Without a current context / GL library both functions throw, like the reference's.
 enum class GraphicsResourceImageType : std::uint8_t { INPUT, OUTPUT };
 
 struct GraphicsResourceImage {
@@ -74,6 +80,12 @@ struct GraphicsResourceImage {
 protected:
 	Image m_Image = {};
 };
+
+#ifdef _WIN32
+// reference core.h:54-59; the Windows / D3D11 build of this library is not provided
+JOSHUPSCALE_EXPORT int getD3D11DeviceIndex(ID3D11Device *d3d11Device);
+JOSHUPSCALE_EXPORT GraphicsResourceImage *getD3D11Image(ID3D11Texture2D *d3d11Texture, GraphicsResourceImageType type);
+#endif
 
 JOSHUPSCALE_EXPORT int getGLDeviceIndex();
 JOSHUPSCALE_EXPORT GraphicsResourceImage *getGLImage(std::uint32_t image, GraphicsResourceImageType type);

@@ -11,7 +11,9 @@
  *        ju_last_error     <- getExceptionString()                       core.h:94
  *        ju_set_log_sink   <- setLogSink(LogSink*)                       core.h:28
  *      plus what the reference does NOT have but the north star needs:
- *        ju_process_batch  (N independent streams advanced in lockstep)
+ *        ju_process_batch  (N independent streams advanced in lockstep; with n < batch images
+ *                           the remaining streams still advance, on stale staging data, and
+ *                           their output is dropped: keep feeding the same leading streams)
  *        ju_reset_state / ju_read_tensor / ju_write_state (recurrent-state
  *        access for oracle comparison; the reference keeps the state private
  *        in TensorRTBackend::m_InterBuffers, tensorrt_backend.cc:213-218)
@@ -97,6 +99,12 @@ JU_API int ju_get_info(const ju_runtime *rt, ju_info *info);
 JU_API const char *ju_last_error(void);
 JU_API void ju_set_log_sink(ju_log_fn fn, void *user);
 JU_API int ju_reset_state(ju_runtime *rt);
+/* Test hook for the failure path: the next frame's tcgen05 kernel `kernel_id` (1 = persistent
+ * trunk) stalls on purpose.  ju_process then fails with "frame aborted: ... wait N expired" once
+ * the wait time-out (JU_WAIT_TIMEOUT_MS, default 4000) has passed, the recurrent state is NOT
+ * advanced and the runtime - and every other runtime of the process - stays usable, like a
+ * failed enqueue in the reference (tensorrt_backend.cc:266, 276-277). */
+JU_API int ju_debug_inject_stall(ju_runtime *rt, int kernel_id);
 JU_API int ju_read_tensor(ju_runtime *rt, const char *name, void *dst, uint64_t capacity, ju_tensor_desc *desc);
 JU_API int ju_write_state(ju_runtime *rt, const char *name, const void *src, uint64_t bytes);
 JU_API int ju_profile_ops(ju_runtime *rt, int iters, ju_op_time *ops, int capacity, int *count);

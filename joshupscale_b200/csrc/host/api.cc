@@ -2,6 +2,7 @@
 // over the sm_100a engine.
 #include <cuda_fp16.h>
 #include <cxxabi.h>
+#include <dlfcn.h>
 
 #include <chrono>
 #include <cstdio>
@@ -69,21 +70,20 @@ namespace {
 using ::JoshUpscale::core::LogLevel;
 using ::JoshUpscale::core::LogSink;
 
+// Default sink, like the reference's console sink (core/src/logging.cc:50-62): every level goes
+// to stderr as "<timestamp with ms> <LEVEL> [<tag>] <message>".
 struct ConsoleSink : LogSink {
 	void operator()(const char *tag, LogLevel level, const std::string &message) override {
 		static const char *names[] = {"INFO", "WARNING", "ERROR"};
-		std::time_t now = std::chrono::system_clock::to_time_t(std::chrono::system_clock::now());
+		const auto now = std::chrono::system_clock::now();
+		const std::time_t secs = std::chrono::system_clock::to_time_t(now);
+		const int ms = static_cast<int>(
+		    std::chrono::duration_cast<std::chrono::milliseconds>(now.time_since_epoch()).count() % 1000);
 		char stamp[32];
 		std::tm tmv{};
-		localtime_r(&now, &tmv);
+		localtime_r(&secs, &tmv);
 		std::strftime(stamp, sizeof(stamp), "%Y-%m-%d %H:%M:%S", &tmv);
-		std::fprintf(stderr, "%s [%s] [%s] %s\n", stamp, names[static_cast<int>(level)], tag, message.c_str());
-	}
-};
-
-struct QuietSink : LogSink {
-	void operator()(const char *tag, LogLevel level, const std::string &message) override {
-		if (level != LogLevel::INFO) ConsoleSink()(tag, level, message);
+		std::fprintf(stderr, "%s.%03d %s [%s] %s\n", stamp, ms, names[static_cast<int>(level)], tag, message.c_str());
 	}
 };
 
@@ -95,7 +95,7 @@ struct CallbackSink : LogSink {
 	}
 };
 
-QuietSink g_DefaultSink;
+ConsoleSink g_DefaultSink;
 CallbackSink g_CallbackSink;
 LogSink *g_Sink = &g_DefaultSink;
 
@@ -159,10 +159,92 @@ Runtime *createRuntime(int deviceId, const std::filesystem::path &modelPath) {
 	return new ::ju::B200Runtime(deviceId, modelPath.string(), 1);
 }
 
-int getGLDeviceIndex() { return -1; }
+// ---- OpenGL interop (reference core/src/core.cc:92-149) --------------------
+// The build machine has no GL headers and the B200 box no display, so nothing here is linked
+// against libGL: the three GL calls the reference makes are resolved from the process's libGL at
+// call time, and the CUDA <-> GL entry points of the CUDA runtime are declared by hand (they are
+// part of cudart; cuda_gl_interop.h only adds the GL typedefs).  Without a current GL context
+// these calls fail exactly like the reference's: with an exception.
+}  // namespace core
+}  // namespace JoshUpscale
 
-GraphicsResourceImage *getGLImage(std::uint32_t, GraphicsResourceImageType) {
-	throw std::runtime_error("OpenGL interop is not available in the headless B200 build");
+extern "C" {
+cudaError_t cudaGraphicsGLRegisterImage(struct cudaGraphicsResource **resource, unsigned int image,
+    unsigned int target, unsigned int flags);
+cudaError_t cudaGLGetDevices(unsigned int *pCudaDeviceCount, int *pCudaDevices, unsigned int cudaDeviceCount,
+    int deviceList);
+}
+
+namespace JoshUpscale {
+namespace core {
+
+namespace {
+
+constexpr unsigned int kGlTexture2D = 0x0DE1, kGlTextureWidth = 0x1000, kGlTextureHeight = 0x1001;
+constexpr int kCudaGLDeviceListAll = 1;  // cudaGLDeviceListAll
+
+struct GlApi {
+	void (*bindTexture)(unsigned int, unsigned int) = nullptr;
+	unsigned int (*getError)() = nullptr;
+	void (*getTexLevelParameteriv)(unsigned int, int, unsigned int, int *) = nullptr;
+
+	static const GlApi &get() {
+		static const GlApi api = [] {
+			GlApi a;
+			void *lib = nullptr;
+			for (const char *name : {"libGL.so.1", "libGL.so", "libOpenGL.so.0"}) {
+				lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+				if (lib) break;
+			}
+			if (!lib) throw std::runtime_error("OpenGL library not found (libGL.so.1)");
+			a.bindTexture = reinterpret_cast<decltype(a.bindTexture)>(dlsym(lib, "glBindTexture"));
+			a.getError = reinterpret_cast<decltype(a.getError)>(dlsym(lib, "glGetError"));
+			a.getTexLevelParameteriv =
+			    reinterpret_cast<decltype(a.getTexLevelParameteriv)>(dlsym(lib, "glGetTexLevelParameteriv"));
+			if (!a.bindTexture || !a.getError || !a.getTexLevelParameteriv) {
+				throw std::runtime_error("OpenGL library lacks glBindTexture / glGetError / glGetTexLevelParameteriv");
+			}
+			return a;
+		}();
+		return api;
+	}
+};
+
+struct GLResourceImage final : GraphicsResourceImage {
+	GLResourceImage(std::uint32_t image, GraphicsResourceImageType type) {
+		const GlApi &gl = GlApi::get();
+		const unsigned int flags = type == GraphicsResourceImageType::INPUT ? cudaGraphicsRegisterFlagsReadOnly
+		                                                                    : cudaGraphicsRegisterFlagsWriteDiscard;
+		gl.bindTexture(kGlTexture2D, image);
+		const unsigned int error = gl.getError();
+		if (error != 0) throw std::runtime_error("Failed to bind texture: " + std::to_string(error));
+		int width = 0, height = 0;
+		gl.getTexLevelParameteriv(kGlTexture2D, 0, kGlTextureWidth, &width);
+		gl.getTexLevelParameteriv(kGlTexture2D, 0, kGlTextureHeight, &height);
+		gl.bindTexture(kGlTexture2D, 0);
+		if (width <= 0 || height <= 0) throw std::runtime_error("texture has no level-0 image");
+		cudaGraphicsResource_t resource = nullptr;
+		::ju::checkCuda(cudaGraphicsGLRegisterImage(&resource, image, kGlTexture2D, flags), "cudaGraphicsGLRegisterImage");
+		m_Image.location = DataLocation::GRAPHICS_RESOURCE;
+		m_Image.ptr = resource;
+		m_Image.width = static_cast<std::size_t>(width);
+		m_Image.height = static_cast<std::size_t>(height);
+	}
+	~GLResourceImage() override { cudaGraphicsUnregisterResource(static_cast<cudaGraphicsResource_t>(m_Image.ptr)); }
+};
+
+}  // namespace
+
+int getGLDeviceIndex() {
+	int device = -1;
+	unsigned int count = 0;
+	::ju::checkCuda(cudaGLGetDevices(&count, &device, 1, kCudaGLDeviceListAll), "cudaGLGetDevices");
+	if (count != 1) throw std::runtime_error("Failed to determine CUDA device");
+	return device;
+}
+
+GraphicsResourceImage *getGLImage(std::uint32_t image, GraphicsResourceImageType type) {
+	return new GLResourceImage(image, type);
 }
 
 }  // namespace core
@@ -234,6 +316,13 @@ void ju_set_log_sink(ju_log_fn fn, void *user) {
 	ju::g_CallbackSink.fn = fn;
 	ju::g_CallbackSink.user = user;
 	ju::setLogSinkInternal(fn ? &ju::g_CallbackSink : nullptr);
+}
+
+int ju_debug_inject_stall(ju_runtime *rt, int kernel_id) {
+	return guarded([&] {
+		if (!rt) throw std::invalid_argument("null argument");
+		rt->impl->engine.injectStall(kernel_id);
+	});
 }
 
 int ju_reset_state(ju_runtime *rt) {
@@ -350,12 +439,8 @@ int ju_launch_conv(int impl, const void *in, const void *weights, const float *b
 			JU_CUDA(ju::launch_conv_simt(a, s));
 		} else if (impl == 1) {
 			ju::ConvTcLaunch l;
-			JU_CUDA(ju::conv_tc_prepare(a, ju::conv_tc_get_variant(), &l));
+			JU_CUDA(ju::conv_tc_prepare(a, ju::conv_tc_default_options(), &l));
 			JU_CUDA(ju::conv_tc_launch(l, nullptr, s));
-		} else if (impl == 2) {
-			ju::ConvTcLaunch l;
-			JU_CUDA(ju::conv_tc2_prepare(a, &l));
-			JU_CUDA(ju::conv_tc2_launch(l, nullptr, s));
 		} else {
 			throw std::invalid_argument("unknown conv impl");
 		}
@@ -366,13 +451,13 @@ int ju_set_option(const char *key, int value) {
 	return guarded([&] {
 		if (!key) throw std::invalid_argument("null key");
 		if (std::strcmp(key, "tc_variant") == 0) {
-			ju::conv_tc_set_variant(value);
+			ju::conv_tc_default_options().variant = value;
 		} else if (std::strcmp(key, "tc_tma_epilogue") == 0) {
-			ju::conv_tc_set_flags(value, -1);
+			ju::conv_tc_default_options().tma_epilogue = value;
 		} else if (std::strcmp(key, "tc_pdl") == 0) {
-			ju::conv_tc_set_flags(-1, value);
+			ju::conv_tc_default_options().pdl = value;
 		} else if (std::strcmp(key, "tc_dual") == 0) {
-			ju::conv_tc_set_dual(value);
+			ju::conv_tc_default_options().dual = value;
 		} else {
 			throw std::invalid_argument(std::string("unknown option ") + key);
 		}
@@ -411,13 +496,10 @@ int ju_bench_conv(int impl, int batch, int h, int w, int cin, int cout, int ksiz
 		JU_CUDA(cudaEventCreate(&e0));
 		JU_CUDA(cudaEventCreate(&e1));
 		ju::ConvTcLaunch l;
-		if (impl == 1) JU_CUDA(ju::conv_tc_prepare(a, ju::conv_tc_get_variant(), &l));
-		if (impl == 2) JU_CUDA(ju::conv_tc2_prepare(a, &l));
+		if (impl == 1) JU_CUDA(ju::conv_tc_prepare(a, ju::conv_tc_default_options(), &l));
 		auto launch = [&] {
 			if (impl == 1) {
 				JU_CUDA(ju::conv_tc_launch(l, nullptr, nullptr));
-			} else if (impl == 2) {
-				JU_CUDA(ju::conv_tc2_launch(l, nullptr, nullptr));
 			} else {
 				JU_CUDA(ju::launch_conv_simt(a, nullptr));
 			}
@@ -442,7 +524,7 @@ int64_t ju_pack_conv_weights(int impl, const float *kernel, const float *scale, 
 		if (dst) ju::conv_simt_pack_weights(kernel, scale, ksize, cin, cin_padded, cout, static_cast<__half *>(dst));
 		return bytes;
 	}
-	if ((impl == 1 || impl == 2) && cin_padded % 64 == 0) {
+	if (impl == 1 && cin_padded % 64 == 0) {
 		auto bytes = static_cast<int64_t>(ju::conv_tc_weight_bytes(ksize, cin_padded, cout));
 		if (dst) ju::conv_tc_pack_weights(kernel, scale, ksize, cin, cin_padded, cout, static_cast<__half *>(dst));
 		return bytes;

@@ -30,6 +30,11 @@ struct ModelException : std::runtime_error {
 	using std::runtime_error::runtime_error;
 };
 
+// a tcgen05 pipeline wait expired (kernels.h: TcStatus); the frame is lost, the runtime is not
+struct KernelStallException : std::runtime_error {
+	using std::runtime_error::runtime_error;
+};
+
 inline void checkCuda(cudaError_t err, const char *what) {
 	if (err != cudaSuccess) {
 		(void) cudaGetLastError();  // clear the sticky-less error state

@@ -4,8 +4,19 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 namespace ju {
+
+const char *tc_kernel_name(int id) {
+	switch (id) {
+	case TC_KERNEL_TRUNK: return "trunk_df_tc_kernel";
+	case TC_KERNEL_CONV: return "conv_tc_kernel";
+	case TC_KERNEL_TAIL: return "tail_tc_kernel";
+	case TC_KERNEL_FLOW: return "flow_df_tc_kernel";
+	default: return "tcgen05 kernel";
+	}
+}
 
 namespace {
 
@@ -19,6 +30,17 @@ int pad16(int c) { return (c + 15) / 16 * 16; }
 int envInt(const char *name, int fallback) {
 	const char *v = std::getenv(name);
 	return v ? std::atoi(v) : fallback;
+}
+
+// Frames of all engines on one device are serialised inside the process.  The persistent trunk
+// kernel has inter-CTA dependencies (trunk_df_tc.cu): all of its CTAs must be resident together,
+// which holds when a frame has the device to itself (grid <= SM count, one CTA per SM) but not
+// when two engines driven from two threads interleave their 227 KB-per-CTA kernels.  The trunks
+// fill every SM anyway, so nothing is lost by taking turns.  (Other processes sharing the GPU
+// through MPS are covered by JU_TRUNK_COOP=1, a cooperative launch.)
+std::mutex &deviceMutex(int device) {
+	static std::mutex mutexes[64];
+	return mutexes[device >= 0 && device < 64 ? device : 63];
 }
 
 }  // namespace
@@ -38,12 +60,15 @@ Engine::Engine(const ModelFile &model, int device, int batch)
 	}
 	m_SmCount = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 1;
 	m_ConvImpl = envInt("JU_CONV_IMPL", 1);  // 1 = tcgen05 (default), 0 = SIMT reference kernels
-	if (const char *v = std::getenv("JU_TC_VARIANT")) conv_tc_set_variant(std::atoi(v));
-	if (const char *v = std::getenv("JU_TC_TMA_EPILOGUE")) conv_tc_set_flags(std::atoi(v), -1);
-	if (const char *v = std::getenv("JU_TC_PDL")) conv_tc_set_flags(-1, std::atoi(v));
-	if (const char *v = std::getenv("JU_TC_DUAL")) conv_tc_set_dual(std::atoi(v));
+	// kernel options belong to this engine: process defaults (ju_set_option), then the environment
+	m_TcOpt = conv_tc_default_options();
+	m_TcOpt.variant = envInt("JU_TC_VARIANT", m_TcOpt.variant);
+	m_TcOpt.tma_epilogue = envInt("JU_TC_TMA_EPILOGUE", m_TcOpt.tma_epilogue);
+	m_TcOpt.pdl = envInt("JU_TC_PDL", m_TcOpt.pdl);
+	m_TcOpt.dual = envInt("JU_TC_DUAL", m_TcOpt.dual);
 	m_UseGraph = envInt("JU_NO_GRAPH", 0) == 0;
-	m_Conv2Cta = envInt("JU_CONV_2CTA", 0) != 0;
+	m_TrunkCooperative = envInt("JU_TRUNK_COOP", 0) != 0;
+	m_WaitTimeoutMs = envInt("JU_WAIT_TIMEOUT_MS", 0);
 	JU_CUDA(cudaStreamCreateWithFlags(&m_Stream, cudaStreamNonBlocking));
 	JU_CUDA(cudaStreamCreateWithFlags(&m_CopyStream, cudaStreamNonBlocking));
 	try {
@@ -100,7 +125,15 @@ Engine::Engine(const ModelFile &model, int device, int batch)
 }
 
 Engine::~Engine() {
+	int prev = -1;
+	cudaGetDevice(&prev);
 	cudaSetDevice(m_Device);
+	struct Restore {  // the caller's current device survives the destructor (reference cuda.h:297-308)
+		int dev;
+		~Restore() {
+			if (dev >= 0) cudaSetDevice(dev);
+		}
+	} restore{prev};
 	cudaStreamSynchronize(m_Stream);
 	cudaStreamSynchronize(m_CopyStream);
 	destroyGraphsAndEvents();
@@ -235,7 +268,10 @@ void Engine::registerTensor(const std::string &name, void *p0, void *p1, int dty
 void Engine::allocate() {
 	const ModelSpec &s = m_Spec;
 	const std::uint64_t B = m_Batch, H = s.frameH, W = s.frameW, PH = s.padH, PW = s.padW;
-	m_TcError = DeviceBuffer(sizeof(int));
+	m_Status = DeviceBuffer(sizeof(TcStatus));
+	m_StatusHost = PinnedBuffer(sizeof(int));
+	*m_StatusHost.as<int>() = 0;
+	uploadStatus(0);
 	m_Brightness = DeviceBuffer(sizeof(float) * B);
 	m_IoHost = PinnedBuffer(sizeof(FrameIO) * B);
 	m_IoDev = DeviceBuffer(sizeof(FrameIO) * B);
@@ -322,27 +358,24 @@ Op Engine::convOp(ConvLayer *L, const __half *in, int cinStride, const __half *r
 		t.weights = L->wTc.get();
 		t.cin = pad64(L->cinReal);
 		t.cin_live = L->cinReal;
-		if (t.cin <= cinStride && m_Conv2Cta && conv_tc2_supported(t)) {
-			// experimental CTA-pair kernel (JU_CONV_2CTA=1): only faster at batch 1, see DESIGN.md 6
-			ConvTcLaunch launch;
-			checkCuda(conv_tc2_prepare(t, &launch), "conv_tc2_prepare");
-			int *err = m_TcError.as<int>();
-			op.run = [launch, err](cudaStream_t s) { return conv_tc2_launch(launch, err, s); };
-			++m_TcOps;
-			return op;
-		}
 		if (t.cin <= cinStride && conv_tc_supported(t)) {
 			ConvTcLaunch launch;
-			cudaError_t prep = conv_tc_prepare(t, conv_tc_get_variant(), &launch);
+			cudaError_t prep = conv_tc_prepare(t, m_TcOpt, &launch);
 			if (pool && prep != cudaSuccess) throw PoolFusionUnavailable();
 			checkCuda(prep, "conv_tc_prepare");
-			int *err = m_TcError.as<int>();
-			op.run = [launch, err](cudaStream_t s) { return conv_tc_launch(launch, err, s); };
+			TcStatus *status = m_Status.as<TcStatus>();
+			op.run = [launch, status](cudaStream_t s) { return conv_tc_launch(launch, status, s); };
 			++m_TcOps;
 			return op;
 		}
 	}
 	if (pool) throw PoolFusionUnavailable();
+	if (m_ConvImpl == 1 && m_BuildVariant == 0 && m_WarnedSimt.insert(L->name).second) {
+		// never silent: this layer runs at a few percent of the tensor-core kernel's speed
+		JU_LOG_WARN << L->name << " (" << L->ksize << "x" << L->ksize << ", " << L->cinReal << " -> " << L->cout
+		            << " channels) has no tcgen05 kernel (needs Cout = 32 or a multiple of 64): running the "
+		               "CUDA-core reference convolution";
+	}
 	op.run = [a](cudaStream_t s) { return launch_conv_simt(a, s); };
 	return op;
 }
@@ -456,7 +489,7 @@ void Engine::buildPlan(int parity, int variant) {
 		if (s.flowFilters.size() % 2) conv("flow/conv_1");
 	} else {
 		const bool flowTrunk = m_ConvImpl == 1 && s.flowFilters[0] == 64 && s.flowFilters[1] > 0 &&
-		                       envInt("JU_FUSED_TRUNK", 1) != 0 && !m_Conv2Cta;
+		                       envInt("JU_FUSED_TRUNK", 1) != 0;
 		if (flowTrunk) {
 			// get_flow_resnet (models.py:257-331) is conv_1 + a ResBlock stack of the generator's shape:
 			// the same persistent trunk kernel runs it
@@ -497,10 +530,10 @@ void Engine::buildPlan(int parity, int variant) {
 	__half *t0 = m_Trunk[0].as<__half>(), *t1 = m_Trunk[1].as<__half>(), *t2 = m_Trunk[2].as<__half>();
 	__half *cur = t0, *tmp = t1, *nxt = t2;
 	const bool fusedTrunk = m_ConvImpl == 1 && s.genFilters == 64 && s.genBlocks > 0 && gs % 64 == 0 &&
-	                        envInt("JU_FUSED_TRUNK", 1) != 0 && !m_Conv2Cta;
+	                        envInt("JU_FUSED_TRUNK", 1) != 0;
 	// conv_1 runs as layer 0 of the dataflow trunk when it can (emitTrunk decides the same way)
 	ConvLayer *gc1 = layer("generator/conv_1");
-	const bool conv1InTrunk = fusedTrunk && envInt("JU_TRUNK_SYNC", -1) != 0 && envInt("JU_TRUNK_LEAD", 1) != 0 &&
+	const bool conv1InTrunk = fusedTrunk && envInt("JU_TRUNK_LEAD", 1) != 0 &&
 	                          gc1->wTc.get() && gc1->cout == 64 && gc1->ksize == 3 && gs == 64;
 	if (!conv1InTrunk) plan.push_back(convOp(gc1, m_GenIn.as<__half>(), 64, nullptr, t0, gs, H, W, false));
 	if (fusedTrunk) {
@@ -577,11 +610,9 @@ __half *Engine::emitTrunk(std::vector<Op> &plan, TrunkState &ts, const std::stri
     ConvLayer *lead, const __half *leadIn, const std::function<void(const __half *, int, int, bool)> &afterChunk) {
 	const int B = m_Batch;
 	const int nBlockLayers = 2 * nBlocks;
-	const int syncMode = envInt("JU_TRUNK_SYNC", -1);
-	const bool dataflow = syncMode != 0;
 	// optional plain conv in front of the ResBlocks (the generator's conv_1): same 3x3 64->64 shape
 	// once its 51 input channels are padded, so it becomes layer 0 of the dataflow trunk
-	if (lead && !(dataflow && envInt("JU_TRUNK_LEAD", 1) != 0 && lead->wTc.get() && lead->cout == 64 && lead->ksize == 3 &&
+	if (lead && !(envInt("JU_TRUNK_LEAD", 1) != 0 && lead->wTc.get() && lead->cout == 64 && lead->ksize == 3 &&
 	                 lead->cinReal <= 64 && cstride == 64)) {
 		lead = nullptr;
 	}
@@ -627,15 +658,13 @@ __half *Engine::emitTrunk(std::vector<Op> &plan, TrunkState &ts, const std::stri
 	ta.act = first->act;
 	ta.slope = first->slope;
 	ta.lead_in = lead ? leadIn : nullptr;
-	// JU_TRUNK_SYNC: 0 = grid barrier per layer (trunk_tc.cu), otherwise (default) per-wave dataflow
-	// counters (trunk_df_tc.cu).
-	// JU_TRUNK_SUBBATCH: with the dataflow trunk a large batch runs as consecutive launches of this
+	// JU_TRUNK_SUBBATCH: a large batch runs as consecutive launches of this
 	// many streams, each through ALL layers, so that the three trunk tensors of one launch stay
 	// resident in L2 (2 PSP streams = 100 MB of the 126 MB; one launch over 16 streams would
 	// stream ~800 MB per layer through HBM).  Default (-1): as many streams as fit 85 % of the
 	// L2; 0 = one launch for the whole batch.
 	const std::size_t perStream = static_cast<std::size_t>(H) * W * cstride;
-	int chunk = dataflow ? envInt("JU_TRUNK_SUBBATCH", -1) : 0;
+	int chunk = envInt("JU_TRUNK_SUBBATCH", -1);
 	if (chunk < 0) {
 		int l2 = 0;
 		cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, m_Device);
@@ -647,7 +676,8 @@ __half *Engine::emitTrunk(std::vector<Op> &plan, TrunkState &ts, const std::stri
 	const std::size_t tilesPerStream = static_cast<std::size_t>((H + 15) / 16) * ((W + 7) / 8);
 	__half *result = trunk_output_buffer(nBlockLayers) == 0 ? t0 : t2;
 	const double leadFlops = lead ? 2.0 * H * W * 9.0 * lead->cinReal * 64 : 0.0;
-	int *err = m_TcError.as<int>();
+	TcStatus *status = m_Status.as<TcStatus>();
+	ta.cooperative = m_TrunkCooperative ? 1 : 0;
 	for (int b0 = 0; b0 < B; b0 += chunk) {
 		TrunkArgs sub = ta;
 		sub.batch = std::min(chunk, B - b0);
@@ -656,16 +686,14 @@ __half *Engine::emitTrunk(std::vector<Op> &plan, TrunkState &ts, const std::stri
 		sub.flags = ta.flags + static_cast<std::size_t>(nLayers) * tilesPerStream * b0;
 		if (lead) sub.lead_in = leadIn + perStream * b0;
 		TrunkTcLaunch launch;
-		checkCuda(dataflow ? trunk_df_tc_prepare(sub, &launch) : trunk_tc_prepare(sub, &launch), "trunk_tc_prepare");
+		checkCuda(trunk_df_tc_prepare(sub, &launch), "trunk_df_tc_prepare");
 		Op op;
 		op.name = prefix + "/block_*(persistent)";
 		op.tensorBound = true;
 		op.layers = b0 == 0 ? nLayers : 0;  // network layers are counted once, not once per sub-batch
 		op.flops = 2.0 * sub.batch * H * W * 9.0 * 64 * 64 * nBlockLayers + sub.batch * leadFlops;
 		op.bytes = static_cast<double>(sub.batch) * H * W * 64 * 2.0 * (2.0 * nLayers + 0.5 * nLayers);
-		op.run = [launch, err, dataflow](cudaStream_t st) {
-			return dataflow ? trunk_df_tc_launch(launch, err, st) : trunk_tc_launch(launch, err, st);
-		};
+		op.run = [launch, status](cudaStream_t st) { return trunk_df_tc_launch(launch, status, st); };
 		plan.push_back(std::move(op));
 		++m_TcOps;
 		if (afterChunk) afterChunk(result, b0, sub.batch, chunk >= B);
@@ -700,7 +728,7 @@ void Engine::emitTail(std::vector<Op> &plan, int parity, const __half *trunkOut,
 	ta.act = ct1->act;
 	ta.slope = ct1->slope;
 	ta.pdl = 1;
-	int *err = m_TcError.as<int>();
+	TcStatus *status = m_Status.as<TcStatus>();
 	const int tileRows = (H + 15) / 16;
 	const int bands = (m_BuildVariant == 1 && nb == 1 && m_Batch == 1 && !m_FilterOn) ? std::min(m_TailBands, tileRows) : 1;
 	for (int band = 0; band < bands; ++band) {
@@ -719,7 +747,7 @@ void Engine::emitTail(std::vector<Op> &plan, int parity, const __half *trunkOut,
 		// read trunk (64ch fp16) + LR input + write BGRX u8 + fp16 state (3ch), SURVEY 8(d)
 		op.bytes = share * nb * (H * W * 64 * 2.0 + H * W * 4.0 + 16.0 * H * W * (4 + 3 * 2));
 		op.flops = share * 2.0 * nb * H * W * (64.0 * 128 + 4.0 * 32 * 12);
-		op.run = [launch, err](cudaStream_t st) { return tail_tc_launch(launch, err, st); };
+		op.run = [launch, status](cudaStream_t st) { return tail_tc_launch(launch, status, st); };
 		plan.push_back(std::move(op));
 		++m_TcOps;
 		if (bands > 1) plan.push_back(chunkDoneOp(b0, nb, 64 * r0, std::min(64 * r1, 4 * H)));
@@ -805,6 +833,25 @@ void Engine::bindImages(int n, const ju_image *inputs, const ju_image *outputs) 
 	FrameIO *io = m_IoHost.as<FrameIO>();
 	m_LastOutputs.assign(outputs, outputs + n);
 	m_OutputNeedsCopy.assign(n, false);
+	m_OutputArrays.assign(n, nullptr);
+	// GRAPHICS_RESOURCE images (reference core/src/cuda_convert.cc.cu:381-397, 420-436): ptr is a
+	// registered cudaGraphicsResource_t (getGLImage / getD3D11Image); it is mapped for the duration
+	// of the frame and its array copied to / from the staging buffers on the frame's stream
+	auto mappedArray = [&](void *ptr, std::size_t w, std::size_t h) -> cudaArray_t {
+		auto res = static_cast<cudaGraphicsResource_t>(ptr);
+		JU_CUDA(cudaGraphicsMapResources(1, &res, m_Stream));
+		m_MappedResources.push_back(res);
+		cudaArray_t array = nullptr;
+		JU_CUDA(cudaGraphicsSubResourceGetMappedArray(&array, res, 0, 0));
+		cudaChannelFormatDesc fmt{};
+		cudaExtent extent{};
+		JU_CUDA(cudaArrayGetInfo(&fmt, &extent, nullptr, array));
+		if (extent.width != w || extent.height != h || fmt.f != cudaChannelFormatKindUnsigned || fmt.x != 8 ||
+		    fmt.y != 8 || fmt.z != 8 || fmt.w != 8) {
+			throw std::invalid_argument("graphics resource must be a 4 x 8-bit image of the model's size");
+		}
+		return array;
+	};
 	for (int s = 0; s < m_Batch; ++s) {
 		std::uint8_t *inStage = m_InStage.as<std::uint8_t>() + s * H * inRow;
 		std::uint8_t *outStage = m_OutStage.as<std::uint8_t>() + s * 4 * H * outRow;
@@ -844,10 +891,20 @@ void Engine::bindImages(int n, const ju_image *inputs, const ju_image *outputs) 
 				f.in_stride = -static_cast<long long>(inRow);
 			}
 		} else if (in.location == JU_LOC_CUDA) {
+			// the kernels read / write whole BGRX pixels: 4-byte aligned rows of at least one row of pixels
+			if (absStride(in.stride) < inRow) throw std::invalid_argument("input stride smaller than a row");
+			if ((reinterpret_cast<std::uintptr_t>(in.ptr) | absStride(in.stride)) & 3u) {
+				throw std::invalid_argument("CUDA input image must be 4-byte aligned (pointer and stride)");
+			}
 			f.in = static_cast<const std::uint8_t *>(in.ptr);
 			f.in_stride = in.stride;
+		} else if (in.location == JU_LOC_GRAPHICS_RESOURCE) {
+			cudaArray_t array = mappedArray(in.ptr, W, H);
+			JU_CUDA(cudaMemcpy2DFromArrayAsync(inStage, inRow, array, 0, 0, inRow, H, cudaMemcpyDeviceToDevice, m_Stream));
+			f.in = inStage;
+			f.in_stride = static_cast<long long>(inRow);
 		} else {
-			throw std::invalid_argument("GRAPHICS_RESOURCE images need a GL/D3D11 build (headless B200 build)");
+			throw std::invalid_argument("unknown image location");
 		}
 		if (out.location == JU_LOC_CPU) {
 			if (absStride(out.stride) < outRow) throw std::invalid_argument("output stride smaller than a row");
@@ -860,10 +917,18 @@ void Engine::bindImages(int n, const ju_image *inputs, const ju_image *outputs) 
 				f.out_stride = -static_cast<long long>(outRow);
 			}
 		} else if (out.location == JU_LOC_CUDA) {
+			if (absStride(out.stride) < outRow) throw std::invalid_argument("output stride smaller than a row");
+			if ((reinterpret_cast<std::uintptr_t>(out.ptr) | absStride(out.stride)) & 3u) {
+				throw std::invalid_argument("CUDA output image must be 4-byte aligned (pointer and stride)");
+			}
 			f.out = static_cast<std::uint8_t *>(out.ptr);
 			f.out_stride = out.stride;
+		} else if (out.location == JU_LOC_GRAPHICS_RESOURCE) {
+			m_OutputArrays[s] = mappedArray(out.ptr, 4 * W, 4 * H);
+			f.out = outStage;
+			f.out_stride = static_cast<long long>(outRow);
 		} else {
-			throw std::invalid_argument("GRAPHICS_RESOURCE images need a GL/D3D11 build (headless B200 build)");
+			throw std::invalid_argument("unknown image location");
 		}
 	}
 	// the device-side address table only changes when the caller's pointers do: host images always
@@ -875,9 +940,44 @@ void Engine::bindImages(int n, const ju_image *inputs, const ju_image *outputs) 
 	}
 }
 
+void Engine::uploadStatus(int inject) {
+	TcStatus st{};
+	st.code = 0;
+	st.timeout_ms = m_WaitTimeoutMs;
+	st.inject = inject;
+	st.host_code = m_StatusHost.as<int>();  // pinned host memory is device-addressable (unified addressing)
+	JU_CUDA(cudaMemcpy(m_Status.get(), &st, sizeof(st), cudaMemcpyHostToDevice));
+}
+
+void Engine::injectStall(int kernelId) {
+	DeviceGuard guard(m_Device);
+	JU_CUDA(cudaStreamSynchronize(m_Stream));
+	uploadStatus(kernelId);
+}
+
+// A pipeline wait expired during the frame (TcStatus): the kernels drained without side effects.
+// Re-arm everything the aborted frame may have left half-way - the status block and the
+// never-reset dataflow counters of the persistent trunks - so that the next frame starts clean.
+void Engine::recoverFromStall() {
+	*m_StatusHost.as<int>() = 0;
+	uploadStatus(0);
+	for (TrunkState *ts : {&m_GenTrunk, &m_FlowTrunk}) {
+		if (ts->counter.get()) JU_CUDA(cudaMemset(ts->counter.get(), 0, ts->counter.bytes()));
+		if (ts->flags.get()) JU_CUDA(cudaMemset(ts->flags.get(), 0, ts->flags.bytes()));
+	}
+}
+
+void Engine::unmapResources() {
+	if (m_MappedResources.empty()) return;
+	std::vector<cudaGraphicsResource_t> res;
+	res.swap(m_MappedResources);
+	JU_CUDA(cudaGraphicsUnmapResources(static_cast<int>(res.size()), res.data(), m_Stream));
+}
+
 void Engine::process(int n, const ju_image *inputs, const ju_image *outputs) {
 	if (n < 1 || n > m_Batch) throw std::invalid_argument("image count must be in [1, batch]");
 	DeviceGuard guard(m_Device);
+	std::lock_guard<std::mutex> turn(deviceMutex(m_Device));  // see deviceMutex: one frame at a time per device
 	const std::size_t H = m_Spec.frameH, W = m_Spec.frameW, outRow = 4 * W * 4;
 	try {
 		bindImages(n, inputs, outputs);
@@ -923,12 +1023,32 @@ void Engine::process(int n, const ju_image *inputs, const ju_image *outputs) {
 				copied = true;
 			}
 		}
+		// graphics-resource outputs: staging buffer -> mapped array, then unmap, all in stream order
+		for (int s = 0; s < n; ++s) {
+			if (!m_OutputArrays[s]) continue;
+			const std::uint8_t *stage = m_OutStage.as<std::uint8_t>() + s * 4 * H * outRow;
+			JU_CUDA(cudaMemcpy2DToArrayAsync(m_OutputArrays[s], 0, 0, stage, outRow, outRow, 4 * H,
+			    cudaMemcpyDeviceToDevice, m_Stream));
+		}
+		unmapResources();
 		JU_CUDA(cudaStreamSynchronize(m_Stream));
 		if (copied) JU_CUDA(cudaStreamSynchronize(m_CopyStream));
+		const int stall = *static_cast<volatile int *>(m_StatusHost.as<int>());
+		if (stall != 0) {
+			recoverFromStall();
+			throw KernelStallException(std::string("frame aborted: ") + tc_kernel_name(stall >> 8) +
+			                           " pipeline wait " + std::to_string(stall & 0xff) + " expired");
+		}
 	} catch (...) {
-		// a failed frame leaves the ping-pong index unchanged (the reference
-		// flips only after the synchronize, tensorrt_backend.cc:276-277)
+		// a failed frame leaves the ping-pong index unchanged (the reference flips only after the
+		// synchronize, tensorrt_backend.cc:276-277); nothing may still be writing into the caller's
+		// images when the exception leaves this function
+		try {
+			unmapResources();
+		} catch (...) {
+		}
 		cudaStreamSynchronize(m_Stream);
+		cudaStreamSynchronize(m_CopyStream);
 		throw;
 	}
 	m_Parity ^= 1;
@@ -976,6 +1096,7 @@ void Engine::writeState(const std::string &name, const void *srcHost, std::uint6
 std::vector<ju_op_time> Engine::profileOps(int iters) {
 	if (iters < 1) iters = 1;
 	DeviceGuard guard(m_Device);
+	std::lock_guard<std::mutex> turn(deviceMutex(m_Device));
 	JU_CUDA(cudaStreamSynchronize(m_Stream));
 	const std::vector<Op> &plan = m_Plans[0][m_Parity];
 	std::vector<cudaEvent_t> ev(plan.size() + 1);

@@ -13,6 +13,7 @@
 #include <functional>
 #include <map>
 #include <memory>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -78,8 +79,13 @@ public:
 		return n;
 	}
 
-	// n <= batch images; streams beyond n are advanced on their last input.
+	// n <= batch images.  All `batch` streams advance in lockstep through one graph: streams
+	// beyond n are advanced on whatever their staging buffer holds and their output is dropped,
+	// so callers that feed fewer images keep using the same leading streams.
 	void process(int n, const ju_image *inputs, const ju_image *outputs);
+	// test hook: the next frame's kernel `kernelId` (TcKernelId) stalls on purpose; process() then
+	// throws KernelStallException and the runtime stays usable
+	void injectStall(int kernelId);
 	void resetState();
 	void readTensor(const std::string &name, void *dst, std::uint64_t capacity, ju_tensor_desc *desc);
 	void writeState(const std::string &name, const void *src, std::uint64_t bytes);
@@ -104,6 +110,9 @@ private:
 	void registerTensor(const std::string &name, void *p0, void *p1, int dtype,
 	    std::vector<std::uint64_t> dims, std::size_t bytes, bool writable);
 	void bindImages(int n, const ju_image *inputs, const ju_image *outputs);
+	void unmapResources();
+	void uploadStatus(int inject);
+	void recoverFromStall();
 
 	ModelSpec m_Spec;
 	int m_Device = 0;
@@ -111,7 +120,8 @@ private:
 	int m_SmCount = 1;
 	int m_ConvImpl = 0;
 	bool m_UseGraph = true;
-	bool m_Conv2Cta = false;
+	bool m_TrunkCooperative = false;
+	ConvTcOptions m_TcOpt{};
 	int m_Parity = 0;
 	cudaStream_t m_Stream = nullptr;
 	cudaGraphExec_t m_GraphExec[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [variant][parity]
@@ -119,13 +129,18 @@ private:
 	PinnedBuffer m_IoHost;
 	DeviceBuffer m_IoDev;
 	std::vector<unsigned char> m_IoShadow;  // last address table sent to the device
-	DeviceBuffer m_TcError;
+	DeviceBuffer m_Status;      // TcStatus, read by every tcgen05 kernel's waits
+	PinnedBuffer m_StatusHost;  // host-mapped copy of TcStatus::code, checked after every frame
+	int m_WaitTimeoutMs = 0;
 	DeviceBuffer m_Brightness;
 	TrunkState m_GenTrunk, m_FlowTrunk;
 	int m_TcOps = 0;
+	std::set<std::string> m_WarnedSimt;
 	DeviceBuffer m_InStage, m_OutStage;
 	std::vector<ju_image> m_LastOutputs;
 	std::vector<bool> m_OutputNeedsCopy;
+	std::vector<cudaArray_t> m_OutputArrays;                 // per stream: mapped output array or null
+	std::vector<cudaGraphicsResource_t> m_MappedResources;  // mapped for the frame in flight
 
 	DeviceBuffer m_FlowIn[2], m_PreGen[2];
 	DeviceBuffer m_FlowHead, m_GenIn, m_Trunk[3], m_Mid, m_W2, m_B2;

@@ -91,6 +91,15 @@ ModelFile ModelFile::load(const std::string &path) {
 		throw ModelException(
 		    "not a .jup model container (the B200 build does not load TensorRT engines): " + path);
 	}
+	// Nothing in the file is trusted: every size is bounded and every offset checked without
+	// arithmetic that can wrap, so a corrupt or crafted container ends in a ModelException.
+	if (h.headerBytes < sizeof(RawHeader) || h.headerBytes > size) throw ModelException("invalid header size");
+	constexpr std::uint32_t kMaxFrame = 8192, kMaxChannels = 1024, kMaxBlocks = 256, kMaxTensors = 8192;
+	if (h.frameH > kMaxFrame || h.frameW > kMaxFrame || h.padH > kMaxFrame + 256 || h.padW > kMaxFrame + 256 ||
+	    h.flowInputs > 21 || h.genFilters < 1 || h.genFilters > kMaxChannels || h.genBlocks > kMaxBlocks ||
+	    h.nTensors > kMaxTensors) {
+		throw ModelException("model header out of range");
+	}
 	ModelFile m;
 	ModelSpec &s = m.m_Spec;
 	s.frameH = h.frameH;
@@ -113,19 +122,39 @@ ModelFile ModelFile::load(const std::string &path) {
 	    s.flowInputs < 1 || s.flowArch > 1) {
 		throw ModelException("invalid model header");
 	}
-	std::size_t tableEnd = h.headerBytes + static_cast<std::size_t>(h.nTensors) * sizeof(RawEntry);
-	if (tableEnd > size) throw ModelException("truncated tensor table");
+	if (s.flowArch == 1) {
+		// get_flow_resnet: {filters, blocks}
+		if (s.flowFilters.size() != 2 || s.flowFilters[0] < 1 || s.flowFilters[0] > static_cast<int>(kMaxChannels) ||
+		    s.flowFilters[1] < 0 || s.flowFilters[1] > static_cast<int>(kMaxBlocks)) {
+			throw ModelException("flow-resnet header needs {filters, blocks}");
+		}
+	} else {
+		for (int f : s.flowFilters) {
+			if (f < 1 || f > static_cast<int>(kMaxChannels)) throw ModelException("flow filter count out of range");
+		}
+		// get_flow_autoencoder: n down blocks + n up blocks (+ one trailing conv); the padded frame
+		// must survive n MaxPool2D(2)
+		if (s.flowFilters.size() < 2) throw ModelException("flow-autoencoder header needs at least two filters");
+		const int n = static_cast<int>(s.flowFilters.size()) / 2;
+		if ((s.padH % (1 << n)) != 0 || (s.padW % (1 << n)) != 0) {
+			throw ModelException("padded frame not divisible by 2^blocks");
+		}
+	}
+	const std::size_t tableBytes = static_cast<std::size_t>(h.nTensors) * sizeof(RawEntry);
+	if (tableBytes > size - h.headerBytes) throw ModelException("truncated tensor table");
 	for (std::uint32_t i = 0; i < h.nTensors; ++i) {
 		RawEntry e;
 		std::memcpy(&e, data.data() + h.headerBytes + i * sizeof(RawEntry), sizeof(e));
-		if (e.dtype != 0 || e.ndim > 4 || e.offset + e.nbytes > size) {
+		if (e.dtype != 0 || e.ndim > 4 || e.offset > size || e.nbytes > size - e.offset) {
 			throw ModelException("invalid tensor entry");
 		}
 		HostTensor t;
-		std::size_t count = 1;
+		std::uint64_t count = 1;
 		for (std::uint32_t d = 0; d < e.ndim; ++d) {
+			if (e.dims[d] == 0 || e.dims[d] > (1u << 24)) throw ModelException("tensor dimension out of range");
 			t.dims.push_back(static_cast<int>(e.dims[d]));
 			count *= e.dims[d];
+			if (count > (std::uint64_t{1} << 32)) throw ModelException("tensor too large");
 		}
 		if (count * sizeof(float) != e.nbytes) throw ModelException("tensor size mismatch");
 		t.data.resize(count);

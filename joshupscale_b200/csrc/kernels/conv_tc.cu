@@ -73,7 +73,7 @@ struct TcParams {
 	float slope;
 	int out_f32;
 	int shuffle2;
-	int *error_flag;
+	TcStatus *status;
 };
 
 using namespace tc;
@@ -175,6 +175,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 	if (warp == 0 || (p.dual && warp == 2 + kEpiWarps)) {
 		// ===================== TMA producer =====================
 		if (lane == 0) {
+			Waiter W(p.status, TC_KERNEL_CONV);
 			if (p.b_resident && !second) {
 				mbar_arrive_expect_tx(w_bar, resb_bytes);
 				for (int s = 0; s < taps * p.kb; ++s) {
@@ -190,7 +191,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 				const TileCoord t = decode_tile(p, tile);
 				const int rb = tc & 1;
 				const uint32_t rph = (tc >> 1) & 1;
-				mbar_wait(rempty_bar(rb), rph ^ 1u, p.error_flag, 6);
+				if (!W.wait(rempty_bar(rb), rph ^ 1u, 6)) return;
 				mbar_arrive_expect_tx(rfull_bar(rb), kEpiTile);
 				tma_load_4d(epi_res_base + rb * kEpiTile, &map_r, rfull_bar(rb), t.n0, t.x0, t.y0, t.b);
 			};
@@ -203,7 +204,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 					const int it = tcount * p.kb + kbi;
 					const int s = it % p.stages;
 					const uint32_t ph = (it / p.stages) & 1;
-					mbar_wait(empty_bar(s), ph ^ 1u, p.error_flag, 1);
+					if (!W.wait(empty_bar(s), ph ^ 1u, 1)) continue;
 					const uint32_t stage = smem_base + s * p.stage_bytes;
 					const uint32_t bytes = p.a_box_bytes + (p.b_resident ? 0u : taps * p.b_slice_bytes);
 					mbar_arrive_expect_tx(full_bar(s), bytes);
@@ -235,22 +236,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 			const uint32_t lo_flags = 1u << 16;            // LBO field (unused for swizzled K-major)
 			const uint32_t row_off = static_cast<uint32_t>(p.pitch) * 8u;  // one halo row, in 16-byte units
 			const uint32_t b_slice16 = p.b_slice_bytes >> 4;
+			Waiter W(p.status, TC_KERNEL_CONV);
 			if (p.b_resident) {
-				mbar_wait(w_bar, 0, p.error_flag, 2);
+				W.wait(w_bar, 0, 2);
 			}
 			int tcount = 0;
 			for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
 				if (p.dual && (tcount & 1) != pipe) continue;
 				const int as = tcount & 1;
 				const uint32_t aph = (tcount >> 1) & 1;
-				mbar_wait(tempty_bar(as), aph ^ 1u, p.error_flag, 3);
+				W.wait(tempty_bar(as), aph ^ 1u, 3);
 				tcgen05_fence_after();
 				const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.nt);
 				for (int kbi = 0; kbi < p.kb; ++kbi) {
 					const int it = tcount * p.kb + kbi;
 					const int s = it % p.stages;
 					const uint32_t ph = (it / p.stages) & 1;
-					mbar_wait(full_bar(s), ph, p.error_flag, 4);
+					W.wait(full_bar(s), ph, 4);
+					W.sync_warp();
+					if (W.dead) continue;  // aborted frame: nothing is issued or committed any more
 					tcgen05_fence_after();
 					const uint32_t stage = smem_base + s * p.stage_bytes;
 					const uint32_t a_lo = lo_flags | (stage >> 4);
@@ -303,6 +307,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 		};
 		uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic pointer to the aligned base
 		float bias_reg[32];
+		Waiter W(p.status, TC_KERNEL_CONV);
 		if (p.pdl) grid_dependency_wait();
 		int tcount = 0;
 		for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
@@ -339,13 +344,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 				const uint32_t sw = EPI == 2 ? static_cast<uint32_t>((row >> 1) & 3) : static_cast<uint32_t>(row & 7);
 				uint4 res[4];
 				if (EPI != 3 && p.residual) {
-					mbar_wait(rfull_bar(as), aph, p.error_flag, 7);
+					W.wait(rfull_bar(as), aph, 7);
 					const uint4 *res_row = reinterpret_cast<const uint4 *>(
 					    smem_gen + (epi_res_base - smem_base) + as * kEpiTile + row * kRowB);
 #pragma unroll
 					for (int c = 0; c < 4; ++c) res[c] = res_row[(coff + c) ^ sw];
 				}
-				mbar_wait(tfull_bar(as), aph, p.error_flag, 5);
+				W.wait(tfull_bar(as), aph, 5);
 				tcgen05_fence_after();
 				uint32_t acc[32];
 				const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
@@ -356,7 +361,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 				// TMEM and residual tile are in registers -> hand both back early
 				tcgen05_fence_before();
 				__syncwarp();
-				if (lane == 0) {
+				W.sync_warp();
+				if (lane == 0 && !W.dead) {
 					mbar_arrive(tempty_bar(as));
 					if (EPI != 3 && p.residual) mbar_arrive(rempty_bar(as));
 				}
@@ -437,7 +443,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 				// make the generic-proxy smem writes visible to the TMA (async proxy)
 				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 				group_barrier();
-				if (etid == 0) {
+				if (etid == 0 && !W.dead) {
 					// out-of-range rows/columns of ragged tiles are clipped by the TMA store
 					if (p.pool) {
 						tma_store_4d(&map_c, epi_out_base + as * kEpiTile, t.n0, t.x0 >> 1, t.y0 >> 1, t.b);
@@ -448,7 +454,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 				continue;
 			}
 			if constexpr (EPI == 0) {
-			mbar_wait(tfull_bar(as), aph, p.error_flag, 5);
+			W.wait(tfull_bar(as), aph, 5);
 			tcgen05_fence_after();
 			const int y = t.y0 + (row >> 3), x = t.x0 + (row & 7);
 			const bool valid = y < p.h && x < p.w;
@@ -534,7 +540,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 			// all of this warp's TMEM reads are complete (wait::ld) -> release the stage
 			tcgen05_fence_before();
 			__syncwarp();
-			if (lane == 0) mbar_arrive(tempty_bar(as));
+			W.sync_warp();
+			if (lane == 0 && !W.dead) mbar_arrive(tempty_bar(as));
 			}  // EPI == 0
 		}
 	}
@@ -571,20 +578,30 @@ EncodeTiledFn encodeTiled() {
 	return fn;
 }
 
-int g_TcVariant = 0;
-int g_TcTmaEpi = 1;
-int g_TcPdl = 1;
-int g_TcDual = 1;
+// process defaults (ju_set_option); every engine takes a copy when it is created
+ConvTcOptions g_TcDefaults{0, 1, 1, 1};
+
+// the kernel instance a prepared launch runs
+const void *conv_tc_function(int ks, int tma_epi) {
+	if (ks == 3) {
+		switch (tma_epi) {
+		case 1: return reinterpret_cast<const void *>(conv_tc_kernel<3, 1>);
+		case 2: return reinterpret_cast<const void *>(conv_tc_kernel<3, 2>);
+		case 3: return reinterpret_cast<const void *>(conv_tc_kernel<3, 3>);
+		default: return reinterpret_cast<const void *>(conv_tc_kernel<3, 0>);
+		}
+	}
+	switch (tma_epi) {
+	case 1: return reinterpret_cast<const void *>(conv_tc_kernel<1, 1>);
+	case 2: return reinterpret_cast<const void *>(conv_tc_kernel<1, 2>);
+	case 3: return reinterpret_cast<const void *>(conv_tc_kernel<1, 3>);
+	default: return reinterpret_cast<const void *>(conv_tc_kernel<1, 0>);
+	}
+}
 
 }  // namespace
 
-void conv_tc_set_variant(int v) { g_TcVariant = v; }
-void conv_tc_set_flags(int tma_epilogue, int pdl) {
-	if (tma_epilogue >= 0) g_TcTmaEpi = tma_epilogue;
-	if (pdl >= 0) g_TcPdl = pdl;
-}
-void conv_tc_set_dual(int on) { g_TcDual = on; }
-int conv_tc_get_variant() { return g_TcVariant; }
+ConvTcOptions &conv_tc_default_options() { return g_TcDefaults; }
 
 bool conv_tc_supported(const ConvArgs &a) {
 	if (a.ksize != 1 && a.ksize != 3) return false;
@@ -617,7 +634,8 @@ void conv_tc_pack_weights(const float *kernel, const float *scale, int ksize, in
 	}
 }
 
-cudaError_t conv_tc_prepare(const ConvArgs &a, int variant, ConvTcLaunch *out) {
+cudaError_t conv_tc_prepare(const ConvArgs &a, const ConvTcOptions &opt, ConvTcLaunch *out) {
+	const int variant = opt.variant;
 	if (!conv_tc_supported(a)) return cudaErrorInvalidValue;
 	EncodeTiledFn encode = encodeTiled();
 	if (!encode) return cudaErrorNotSupported;
@@ -668,7 +686,7 @@ cudaError_t conv_tc_prepare(const ConvArgs &a, int variant, ConvTcLaunch *out) {
 	// shared-memory epilogue (TMA residual load + TMA store) for the common
 	// fp16, 64-channel-tile, non-shuffled case
 	p.tma_epi = 0;
-	if (g_TcTmaEpi && !a.shuffle2 && a.cout_stride % 8 == 0) {
+	if (opt.tma_epilogue && !a.shuffle2 && a.cout_stride % 8 == 0) {
 		if (!a.out_f32 && p.nt == 64) p.tma_epi = 1;
 		else if (!a.out_f32 && p.nt == 32) p.tma_epi = 2;
 		else if (a.out_f32 && p.nt == 32 && !a.residual) p.tma_epi = 3;
@@ -696,11 +714,12 @@ cudaError_t conv_tc_prepare(const ConvArgs &a, int variant, ConvTcLaunch *out) {
 	if (stages > kMaxStages) stages = kMaxStages;
 	// dual pipelines need an even stage count (disjoint halves of the ring, see the kernel)
 	p.dual = 0;
-	if (g_TcDual && p.kb == 1 && p.b_resident && !a.residual && stages >= 4) {
+	if (opt.dual && p.kb == 1 && p.b_resident && !a.residual && stages >= 4) {
 		p.dual = 1;
 		stages &= ~1;
 	}
 	p.stages = stages;
+	p.pdl = opt.pdl ? 1 : 0;
 	p.bias = a.bias;
 	p.residual = a.residual;
 	p.out = a.out;
@@ -708,7 +727,7 @@ cudaError_t conv_tc_prepare(const ConvArgs &a, int variant, ConvTcLaunch *out) {
 	p.slope = a.slope;
 	p.out_f32 = a.out_f32;
 	p.shuffle2 = a.shuffle2;
-	p.error_flag = nullptr;
+	p.status = nullptr;
 
 	CUtensorMap mapA, mapB, mapC, mapR;
 	std::memset(&mapC, 0, sizeof(mapC));
@@ -776,26 +795,12 @@ cudaError_t conv_tc_prepare(const ConvArgs &a, int variant, ConvTcLaunch *out) {
 	out->grid = p.total_tiles < sms ? p.total_tiles : sms;
 	out->smem_bytes = fixed + static_cast<uint32_t>(p.stages) * p.stage_bytes;
 	out->pdl = p.pdl;
-	return cudaSuccess;
+	// per device and cheap: set at every prepare (plan time), never on the launch path
+	return cudaFuncSetAttribute(conv_tc_function(p.ks, p.tma_epi), cudaFuncAttributeMaxDynamicSharedMemorySize,
+	    static_cast<int>(kSmemLimit));
 }
 
-cudaError_t conv_tc_launch(const ConvTcLaunch &l, int *error_flag, cudaStream_t s) {
-	static bool attr_set[16] = {false};
-	int dev = 0;
-	cudaGetDevice(&dev);
-	if (dev >= 0 && dev < 16 && !attr_set[dev]) {
-		const void *kernels[8] = {
-		    reinterpret_cast<const void *>(conv_tc_kernel<3, 0>), reinterpret_cast<const void *>(conv_tc_kernel<3, 1>),
-		    reinterpret_cast<const void *>(conv_tc_kernel<3, 2>), reinterpret_cast<const void *>(conv_tc_kernel<3, 3>),
-		    reinterpret_cast<const void *>(conv_tc_kernel<1, 0>), reinterpret_cast<const void *>(conv_tc_kernel<1, 1>),
-		    reinterpret_cast<const void *>(conv_tc_kernel<1, 2>), reinterpret_cast<const void *>(conv_tc_kernel<1, 3>)};
-		for (const void *k : kernels) {
-			cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
-			    static_cast<int>(kSmemLimit));
-			if (e != cudaSuccess) return e;
-		}
-		attr_set[dev] = true;
-	}
+cudaError_t conv_tc_launch(const ConvTcLaunch &l, TcStatus *status, cudaStream_t s) {
 	CUtensorMap mapA, mapB, mapC, mapR;
 	TcParams p;
 	std::memcpy(&mapA, l.map_a, 128);
@@ -803,7 +808,7 @@ cudaError_t conv_tc_launch(const ConvTcLaunch &l, int *error_flag, cudaStream_t 
 	std::memcpy(&mapC, l.map_c, 128);
 	std::memcpy(&mapR, l.map_r, 128);
 	std::memcpy(&p, l.params, sizeof(p));
-	p.error_flag = error_flag;
+	p.status = status;
 	cudaLaunchConfig_t cfg{};
 	cfg.gridDim = dim3(l.grid);
 	cfg.blockDim = dim3(p.tma_epi != 0 ? kThreadsWide : kThreads);
@@ -815,23 +820,7 @@ cudaError_t conv_tc_launch(const ConvTcLaunch &l, int *error_flag, cudaStream_t 
 	cfg.attrs = attr;
 	cfg.numAttrs = l.pdl ? 1 : 0;
 	void *args[5] = {&mapA, &mapB, &mapC, &mapR, &p};
-	const void *fn = nullptr;
-	if (p.ks == 3) {
-		switch (p.tma_epi) {
-		case 1: fn = reinterpret_cast<const void *>(conv_tc_kernel<3, 1>); break;
-		case 2: fn = reinterpret_cast<const void *>(conv_tc_kernel<3, 2>); break;
-		case 3: fn = reinterpret_cast<const void *>(conv_tc_kernel<3, 3>); break;
-		default: fn = reinterpret_cast<const void *>(conv_tc_kernel<3, 0>); break;
-		}
-	} else {
-		switch (p.tma_epi) {
-		case 1: fn = reinterpret_cast<const void *>(conv_tc_kernel<1, 1>); break;
-		case 2: fn = reinterpret_cast<const void *>(conv_tc_kernel<1, 2>); break;
-		case 3: fn = reinterpret_cast<const void *>(conv_tc_kernel<1, 3>); break;
-		default: fn = reinterpret_cast<const void *>(conv_tc_kernel<1, 0>); break;
-		}
-	}
-	return cudaLaunchKernelExC(&cfg, fn, args);
+	return cudaLaunchKernelExC(&cfg, conv_tc_function(p.ks, p.tma_epi), args);
 }
 
 }  // namespace ju

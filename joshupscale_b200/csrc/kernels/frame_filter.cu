@@ -215,8 +215,10 @@ filter_blend_kernel(const __half *__restrict__ out_raw, const __half *__restrict
 			px[j * 4 + 3] = 0;
 			st[j * 4 + 3] = __float2half_rn(0.f);
 		}
-		*reinterpret_cast<uint4 *>(f.out + static_cast<long long>(Y) * f.out_stride + 16ll * x) =
-		    *reinterpret_cast<const uint4 *>(px);
+		// caller images are only guaranteed 4-byte aligned (pointer and stride): four pixel stores
+		uchar4 *odst = reinterpret_cast<uchar4 *>(f.out + static_cast<long long>(Y) * f.out_stride + 16ll * x);
+#pragma unroll
+		for (int j = 0; j < 4; ++j) odst[j] = reinterpret_cast<const uchar4 *>(px)[j];
 		uint4 *sdst = reinterpret_cast<uint4 *>(
 		    pre_gen_next + ((static_cast<size_t>(b) * 4 * h + Y) * 4 * w + 4 * x) * 4);
 		sdst[0] = reinterpret_cast<const uint4 *>(st)[0];

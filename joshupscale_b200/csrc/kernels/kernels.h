@@ -23,6 +23,20 @@ struct FrameIO {
 
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2 };
 
+// Status block of the tcgen05 kernels (device memory, one per engine; see tc_common.cuh).  A
+// pipeline wait that exceeds `timeout_ms` records (kernel id << 8) | wait code here and in the
+// host-mapped word, the kernel drains without side effects and the engine throws after the
+// frame's stream synchronize - a stall is a recoverable exception, not a trap.
+struct TcStatus {
+	int code;         // 0 = ok
+	int timeout_ms;   // 0 = default (4 s)
+	int inject;       // fault injection (tests): id of the kernel whose pipeline stalls on purpose
+	int pad;
+	int *host_code;   // mapped pinned host copy of `code` (may be null)
+};
+enum TcKernelId : int { TC_KERNEL_TRUNK = 1, TC_KERNEL_CONV = 2, TC_KERNEL_TAIL = 3, TC_KERNEL_FLOW = 4 };
+const char *tc_kernel_name(int id);
+
 struct ConvArgs {
 	const __half *in;        // [batch, h, w, cin_stride]
 	const void *weights;     // packed for the chosen impl
@@ -76,25 +90,20 @@ struct ConvTcLaunch {
 	int pdl;
 };
 bool conv_tc_supported(const ConvArgs &a);
-// a.weights must point at DEVICE memory packed by conv_tc_pack_weights with
-// cin_padded == a.cin.  variant: 0 = 18x10-pixel halo box (default),
-// 1 = 18x16-pixel halo box (cross-check layout).
-cudaError_t conv_tc_prepare(const ConvArgs &a, int variant, ConvTcLaunch *out);
-cudaError_t conv_tc_launch(const ConvTcLaunch &l, int *error_flag, cudaStream_t s);
+// variant: 0 = 18x10-pixel halo box (default), 1 = 18x16-pixel halo box (cross-check layout);
+// tma_epilogue: shared-memory epilogue with TMA residual load + TMA store; pdl: programmatic
+// dependent launch; dual: two alternating producer / issuer pipelines where the layer allows.
+struct ConvTcOptions {
+	int variant, tma_epilogue, pdl, dual;
+};
+// process-wide defaults (changed by ju_set_option); engines copy them at creation
+ConvTcOptions &conv_tc_default_options();
+// a.weights must point at DEVICE memory packed by conv_tc_pack_weights with cin_padded == a.cin.
+cudaError_t conv_tc_prepare(const ConvArgs &a, const ConvTcOptions &opt, ConvTcLaunch *out);
+cudaError_t conv_tc_launch(const ConvTcLaunch &l, TcStatus *status, cudaStream_t s);
 size_t conv_tc_weight_bytes(int ksize, int cin_padded, int cout);
 void conv_tc_pack_weights(const float *kernel, const float *scale, int ksize, int cin,
     int cin_padded, int cout, __half *dst);
-// CTA-pair (cta_group::2) variant for 3x3 64->64 fp16 layers (conv_tc2.cu);
-// weights packed by conv_tc_pack_weights
-bool conv_tc2_supported(const ConvArgs &a);
-cudaError_t conv_tc2_prepare(const ConvArgs &a, ConvTcLaunch *out);
-cudaError_t conv_tc2_launch(const ConvTcLaunch &l, int *error_flag, cudaStream_t s);
-void conv_tc_set_variant(int v);
-// -1 keeps the current value.  tma_epilogue: shared-memory epilogue with TMA
-// residual load + TMA store; pdl: programmatic dependent launch.
-void conv_tc_set_flags(int tma_epilogue, int pdl);
-void conv_tc_set_dual(int on);  // two alternating producer / issuer pipelines where the layer allows (default on)
-int conv_tc_get_variant();
 
 // ---- fused generator tail (tail_tc.cu): conv_trans_1 GEMM + conv_trans_2 +
 // tanh + bilinear x4 + add + clip + u8 pack + state write in one kernel ------
@@ -124,9 +133,9 @@ struct TailTcLaunch {
 	int pdl;
 };
 cudaError_t tail_tc_prepare(const TailArgs &a, TailTcLaunch *out);
-cudaError_t tail_tc_launch(const TailTcLaunch &l, int *error_flag, cudaStream_t s);
+cudaError_t tail_tc_launch(const TailTcLaunch &l, TcStatus *status, cudaStream_t s);
 
-// ---- persistent ResBlock trunk (trunk_tc.cu): all 3x3 64->64 layers in one launch
+// ---- persistent ResBlock trunk (trunk_df_tc.cu): all 3x3 64->64 layers in one launch
 struct TrunkArgs {
 	void *buffers[3];        // T0 (input of the first block), T1, T2: [batch, h, w, cstride] fp16
 	int cstride;
@@ -142,6 +151,10 @@ struct TrunkArgs {
 	// generator's conv_1), reading this tensor [batch, h, w, cstride] and writing T0; its weights
 	// and bias come first in `weights` / `bias`
 	const void *lead_in;
+	// launch with cudaLaunchAttributeCooperative: the driver then guarantees that all CTAs of the
+	// grid are resident together, which the inter-CTA dependencies of this kernel need when other
+	// work (another process under MPS, another stream) may occupy SMs
+	int cooperative;
 };
 struct TrunkTcLaunch {
 	alignas(64) unsigned char maps[8 * 128];
@@ -149,12 +162,11 @@ struct TrunkTcLaunch {
 	int grid;
 	unsigned int smem_bytes;
 	unsigned int *sync_counter;
+	int cooperative;
 };
-cudaError_t trunk_tc_prepare(const TrunkArgs &a, TrunkTcLaunch *out);
-cudaError_t trunk_tc_launch(const TrunkTcLaunch &l, int *error_flag, cudaStream_t s);
-// dataflow version (trunk_df_tc.cu): per-tile completion flags instead of the grid barrier
+// (trunk_df_tc.cu) per-wave completion counters between layers, no grid-wide barrier
 cudaError_t trunk_df_tc_prepare(const TrunkArgs &a, TrunkTcLaunch *out);
-cudaError_t trunk_df_tc_launch(const TrunkTcLaunch &l, int *error_flag, cudaStream_t s);
+cudaError_t trunk_df_tc_launch(const TrunkTcLaunch &l, TcStatus *status, cudaStream_t s);
 // index (0 or 2) of the buffer holding the trunk output after n_layers
 inline int trunk_output_buffer(int n_layers) { return ((n_layers / 2) & 1) ? 2 : 0; }
 

@@ -49,7 +49,7 @@ struct TailParams {
 	__half *pre_gen_next;  // [batch,4H,4W,4]
 	float *out_raw;        // optional [batch,4H,4W,3]
 	const float *brightness;  // optional [batch]
-	int *error_flag;
+	TcStatus *status;
 };
 
 // tanh(x) = 1 - 2 / (exp(2x) + 1) with ex2.approx / fast division: absolute error
@@ -138,6 +138,7 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
 	if (warp == 0) {
 		if (lane == 0) {
+			Waiter W(p.status, TC_KERNEL_TAIL);
 			mbar_arrive_expect_tx(w_bar, kBBytes);
 			tma_load_2d(b_base, &map_b, w_bar, 0, 0);
 			if (p.pdl) grid_dependency_wait();
@@ -147,7 +148,7 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 				decode(tile, b, y0, x0);
 				const int s = it % kStages;
 				const uint32_t ph = (it / kStages) & 1;
-				mbar_wait(empty_bar(s), ph ^ 1u, p.error_flag, 1);
+				if (!W.wait(empty_bar(s), ph ^ 1u, 1)) continue;
 				mbar_arrive_expect_tx(full_bar(s), kATile);
 				tma_load_4d(smem_base + s * kATile, &map_a, full_bar(s), 0, x0, y0, b);
 			}
@@ -157,15 +158,16 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 			const uint32_t idesc = make_idesc(128);
 			const uint32_t hi = static_cast<uint32_t>(make_smem_desc(0, 1024u, 0) >> 32);
 			const uint32_t lo_flags = 1u << 16;
-			mbar_wait(w_bar, 0, p.error_flag, 2);
+			Waiter W(p.status, TC_KERNEL_TAIL);
+			W.wait(w_bar, 0, 2);
 			int it = 0;
 			for (int tile = p.tile_begin + blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
 				const int as = it & 1;
 				const uint32_t aph = (it >> 1) & 1;
-				mbar_wait(tempty_bar(as), aph ^ 1u, p.error_flag, 3);
+				W.wait(tempty_bar(as), aph ^ 1u, 3);
 				const int s = it % kStages;
 				const uint32_t ph = (it / kStages) & 1;
-				mbar_wait(full_bar(s), ph, p.error_flag, 4);
+				if (!W.wait(full_bar(s), ph, 4)) continue;  // aborted frame: nothing is issued any more
 				tcgen05_fence_after();
 				const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * 128);
 				const uint32_t a_lo = lo_flags | ((smem_base + s * kATile) >> 4);
@@ -192,6 +194,7 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 		const int row = q4 * 32 + lane;
 		const float *w2s = reinterpret_cast<const float *>(smem_gen + w2_off);
 		const float b2[3] = {w2s[384], w2s[385], w2s[386]};
+		Waiter W(p.status, TC_KERNEL_TAIL);
 		if (p.pdl) grid_dependency_wait();
 		const int H4 = 4 * p.h, W4 = 4 * p.w;
 		int it = 0;
@@ -218,7 +221,7 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 				cr[2][0] = preprocess_px(pbl.x); cr[2][1] = preprocess_px(pbl.y); cr[2][2] = preprocess_px(pbl.z);
 				cr[3][0] = preprocess_px(pbr.x); cr[3][1] = preprocess_px(pbr.y); cr[3][2] = preprocess_px(pbr.z);
 			}
-			mbar_wait(tfull_bar(as), aph, p.error_flag, 5);
+			W.wait(tfull_bar(as), aph, 5);
 			tcgen05_fence_after();
 			const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) +
 			                       static_cast<uint32_t>(as * 128 + q * 32);
@@ -228,7 +231,8 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 			tmem_ld_wait();
 			tcgen05_fence_before();
 			__syncwarp();
-			if (lane == 0) mbar_arrive(tempty_bar(as));
+			W.sync_warp();
+			if (lane == 0 && !W.dead) mbar_arrive(tempty_bar(as));
 			float m[32];
 #pragma unroll
 			for (int c4 = 0; c4 < 8; ++c4) {
@@ -408,25 +412,18 @@ cudaError_t tail_tc_prepare(const TailArgs &a, TailTcLaunch *out) {
 	out->grid = n_tiles < sms ? n_tiles : sms;
 	out->smem_bytes = kSmemBytes;
 	out->pdl = a.pdl;
-	return cudaSuccess;
+	// per device and cheap: set at every prepare (plan time), never on the launch path
+	return cudaFuncSetAttribute(tail_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	    static_cast<int>(kSmemBytes));
 }
 
-cudaError_t tail_tc_launch(const TailTcLaunch &l, int *error_flag, cudaStream_t s) {
-	static bool attr_set[16] = {false};
-	int dev = 0;
-	cudaGetDevice(&dev);
-	if (dev >= 0 && dev < 16 && !attr_set[dev]) {
-		cudaError_t e = cudaFuncSetAttribute(tail_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-		    static_cast<int>(kSmemBytes));
-		if (e != cudaSuccess) return e;
-		attr_set[dev] = true;
-	}
+cudaError_t tail_tc_launch(const TailTcLaunch &l, TcStatus *status, cudaStream_t s) {
 	CUtensorMap mapA, mapB;
 	TailParams p;
 	std::memcpy(&mapA, l.map_a, 128);
 	std::memcpy(&mapB, l.map_b, 128);
 	std::memcpy(&p, l.params, sizeof(p));
-	p.error_flag = error_flag;
+	p.status = status;
 	cudaLaunchConfig_t cfg{};
 	cfg.gridDim = dim3(l.grid);
 	cfg.blockDim = dim3(kThreads);

@@ -7,6 +7,8 @@
 
 #include <cstdint>
 
+#include "kernels.h"
+
 namespace ju {
 namespace tc {
 
@@ -53,15 +55,78 @@ __device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity
 	return ok;
 }
 
-// Bounded wait: a protocol bug must surface as an error, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int *error_flag, int code) {
-	for (uint32_t i = 0; i < (1u << 22); ++i) {
-		if (mbar_try_wait(bar, parity)) return;
-		if (i > 128) __nanosleep(128);
-	}
-	if (error_flag) atomicExch(error_flag, code);
-	__trap();
+// ---- bounded, abortable waits ----------------------------------------------
+// A protocol bug or a lost dependency must surface as a recoverable error, never as a hung GPU
+// and never as a trap (a trap is a sticky context error that kills every runtime of the host
+// process; the reference reports failures as exceptions, core/src/tensorrt_backend.cc:266).
+//
+// TcStatus lives in device memory, one per engine.  A wait that exceeds `timeout_ms` records its
+// code (also in the host-mapped word the engine reads after the stream synchronize) and the
+// waiting thread turns DEAD: every later wait returns at once and every side effect (TMA, MMA,
+// arrive, publish) is skipped - the control flow itself is unchanged, so named barriers and the
+// final __syncthreads are still reached by everybody and the kernel drains in microseconds.
+// Other threads / CTAs learn about the abort from `code` in the slow path of their own waits.
+constexpr int kTimeoutMsDefault = 4000;
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
 }
+
+struct Waiter {
+	TcStatus *status;
+	int kernel_id;
+	bool dead;
+	__device__ __forceinline__ Waiter(TcStatus *s, int id) : status(s), kernel_id(id), dead(false) {}
+
+	// converged-warp roles: one lane's abort is everybody's
+	__device__ __forceinline__ void sync_warp() { dead = __any_sync(0xffffffffu, dead) != 0; }
+
+	__device__ __forceinline__ void fail(int code) {
+		dead = true;
+		if (!status) return;
+		const int v = (kernel_id << 8) | code;
+		if (atomicCAS(&status->code, 0, v) == 0) {
+			int *h = status->host_code;
+			if (h) {
+				*reinterpret_cast<volatile int *>(h) = v;
+				__threadfence_system();
+			}
+		}
+	}
+
+	// true when the barrier phase completed; false once the frame is aborted
+	__device__ __forceinline__ bool wait(uint32_t bar, uint32_t parity, int code) {
+		if (dead) return false;
+		unsigned long long t0 = 0;
+		for (uint32_t i = 0;; ++i) {
+			if (mbar_try_wait(bar, parity)) return true;
+			if (i < 128u) continue;  // tight polls first: most waits complete within a few hundred ns
+			__nanosleep(128);
+			if (i == 128u) t0 = globaltimer_ns();
+			if ((i & 255u) == 0u && poll_expired(t0, code)) return false;
+		}
+	}
+
+	// a global-memory poll loop (dataflow counters) calls this every few hundred spins
+	__device__ __forceinline__ bool poll_expired(unsigned long long t0, int code) {
+		if (status && *reinterpret_cast<volatile int *>(&status->code) != 0) {
+			dead = true;
+			return true;
+		}
+		unsigned long long limit = static_cast<unsigned long long>(kTimeoutMsDefault) * 1000000ull;
+		if (status) {
+			const int ms = *reinterpret_cast<volatile int *>(&status->timeout_ms);
+			if (ms > 0) limit = static_cast<unsigned long long>(ms) * 1000000ull;
+		}
+		if (globaltimer_ns() - t0 > limit) {
+			fail(code);
+			return true;
+		}
+		return false;
+	}
+};
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0,
     int c1, int c2, int c3) {

@@ -73,7 +73,7 @@ struct TrunkParams {
 	const float *bias;            // [n_layers][64]
 	unsigned int *sync_counter;   // [0] finished-CTA counter, [1] launch epoch
 	unsigned int *flags;          // [n_layers][n_waves] stored-tile counters, never reset
-	int *error_flag;
+	TcStatus *status;
 	const __half *buffers[3];     // T0, T1, T2 (residual rows are read straight from global memory)
 	int cstride;
 	int lead;  // layer 0 is a plain conv reading maps.in[3] and writing T0; ResBlock layers follow
@@ -198,6 +198,7 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 	if (warp == 0 || warp == kSecondProducerWarp) {
 		const int pme = warp == 0 ? 0 : 1;  // two producers, alternating tiles
 		// ===================== TMA producer (warp converged; lanes 0..8 poll neighbour flags) =====
+		Waiter W(p.status, TC_KERNEL_TRUNK);
 		if (p.pdl) grid_dependency_wait();
 		int it = 0;
 		for (int l = 0; l < p.n_layers; ++l) {
@@ -209,13 +210,14 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 				if ((it & 1) != pme) continue;
 				const int s = it % p.stages;
 				const uint32_t ph = (it / p.stages) & 1;
-				mbar_wait(empty_bar(s), ph ^ 1u, p.error_flag, 1);
+				W.wait(empty_bar(s), ph ^ 1u, 1);
+				W.sync_warp();
 				bool polled = false;
-				if (l > 0) {
+				if (l > 0 && !W.dead) {
 					// waves <= k+1 of layer l-1 must be completely stored (covers the 3x3 neighbourhood)
 					const int k = (tile - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x);
 					const int needw = k + wave_reach < n_waves ? k + wave_reach : n_waves - 1;
-					while (known < needw) {
+					while (known < needw && !W.dead) {
 						// lane i polls wave known+1+i: relaxed spins (no L1 invalidation per poll), then one
 						// acquire load per counter once all of them are complete
 						const int wv = known + 1 + lane;
@@ -225,22 +227,28 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 						const unsigned int target = (epoch + 1u) * static_cast<unsigned int>(cntw);
 						const unsigned int *ctr = p.flags + (l - 1) * n_waves + (mine ? wv : 0);
 						unsigned int spins = 0;
+						unsigned long long t0 = 0;
 						while (true) {
 							const bool ok = !mine || static_cast<int>(ld_relaxed_gpu(ctr) - target) >= 0;
 							if (__all_sync(0xffffffffu, ok)) break;
 							if (spins > 64) __nanosleep(32);  // tight relaxed polls first: the dependency is usually a few hundred ns away
-							if (++spins > (1u << 24)) {
-								if (p.error_flag) atomicExch(p.error_flag, 8);
-								__trap();
+							++spins;
+							if (spins == 64u) t0 = globaltimer_ns();
+							// a dependency that never arrives aborts the frame (recoverable), it does not trap
+							const bool expired = (spins & 1023u) == 0u && W.poll_expired(t0, 8);
+							if (__any_sync(0xffffffffu, expired)) {
+								W.dead = true;
+								break;
 							}
 						}
+						if (W.dead) break;
 						if (mine) (void)ld_acquire_gpu(ctr);
 						__syncwarp();
 						known = known + 32 < needw ? known + 32 : needw;
 						polled = true;
 					}
 				}
-				if (lane == 0) {
+				if (lane == 0 && !W.dead) {
 					if (polled) {
 						// order the async-proxy (TMA) reads below after the acquire loads above
 						asm volatile("fence.proxy.async;" ::: "memory");
@@ -254,9 +262,11 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 	} else if (warp == 10) {
 		// ===================== weight loader: tap slices follow the MMA warp layer by layer ======
 		if (lane == 0) {
+			Waiter W(p.status, TC_KERNEL_TRUNK);
 			for (int l = 0; l < p.n_layers; ++l) {
 				for (int t = 0; t < 9; ++t) {
-					if (l > 0) mbar_wait(wempty_tap(t), static_cast<uint32_t>((l - 1) & 1), p.error_flag, 9);
+					if (l > 0) W.wait(wempty_tap(t), static_cast<uint32_t>((l - 1) & 1), 9);
+					if (W.dead) continue;
 					mbar_arrive_expect_tx(wfull_tap(t), kBSlice);
 					tma_load_2d(resb_base + t * kBSlice, &maps.w, wfull_tap(t), 0, (l * 9 + t) * 64);
 				}
@@ -268,6 +278,10 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 		// publish (GPU-scope release, ~1 us) - so no epilogue warp ever waits on a store or a fence,
 		// and the publish latency of one tile overlaps the stores of the next ones.
 		if (lane == 0) {
+			Waiter W(p.status, TC_KERNEL_TRUNK);
+			// test hook: a launch whose status block names this kernel never publishes a tile, i.e.
+			// every consumer of layer 0 stalls until its wait expires
+			const bool stall = p.status && *reinterpret_cast<volatile int *>(&p.status->inject) == TC_KERNEL_TRUNK;
 			if (p.pdl) grid_dependency_wait();
 			const int me = warp - 11;
 			int it = 0;
@@ -279,7 +293,8 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 					decode(tile, b, y0, x0);
 					const int as = me;  // this warp's staging tile
 					const uint32_t aph = (it / kStoreWarps) & 1;
-					mbar_wait(sready_bar(as), aph, p.error_flag, 10);
+					W.wait(sready_bar(as), aph, 10);
+					if (W.dead) continue;
 					tma_store_4d(mout, epi_out_base + as * kEpiTile, 0, x0, y0, b);
 					asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem tile consumed
 					mbar_arrive(sfree_bar(as));
@@ -287,6 +302,7 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 					// the bulk store has completed (async proxy): order it before the generic-proxy
 					// release below, which makes it visible to every acquiring producer warp
 					asm volatile("fence.proxy.async;" ::: "memory");
+					if (stall) continue;
 					asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(
 					                 p.flags + l * n_waves +
 					                 (tile - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x))
@@ -309,6 +325,7 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 		// the other warp's MMAs execute.  Tiles are independent (own TMEM stage, own halo stage);
 		// only the resident weights couple them, see `pos` below.
 		const int mi = warp == 1 ? 0 : 1;
+		Waiter W(p.status, TC_KERNEL_TRUNK);
 		const uint32_t idesc = make_idesc(64);
 		const uint32_t a_hi = static_cast<uint32_t>(make_smem_desc(0, 1280u, 0) >> 32);
 		const uint32_t b_hi = static_cast<uint32_t>(make_smem_desc(0, 1024u, 0) >> 32);
@@ -324,8 +341,9 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 				const uint32_t aph = (it / kAccStages) & 1;
 				const int s = it % p.stages;
 				const uint32_t ph = (it / p.stages) & 1;
-				mbar_wait(tempty_bar(as), aph ^ 1u, p.error_flag, 3);
-				mbar_wait(full_bar(s), ph, p.error_flag, 4);
+				W.wait(tempty_bar(as), aph ^ 1u, 3);
+				W.wait(full_bar(s), ph, 4);
+				W.sync_warp();
 				tcgen05_fence_after();
 				const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * 64);
 				const uint32_t a_lo = lo_flags | ((smem_base + s * kARegion) >> 4);
@@ -337,7 +355,8 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 				if (elect_one_sync()) {
 #pragma unroll
 					for (int tap = 0; tap < 9; ++tap) {
-						if (fresh) mbar_wait(wfull_tap(tap), static_cast<uint32_t>(l & 1), p.error_flag, 2);
+						if (fresh) W.wait(wfull_tap(tap), static_cast<uint32_t>(l & 1), 2);
+						if (W.dead) break;  // aborted frame: nothing is issued or committed any more
 						const uint32_t a_tap = a_lo + (tap / 3) * 80u + (tap % 3) * 8u;
 						const uint32_t b_tap = b_lo + tap * (kBSlice >> 4);
 #pragma unroll
@@ -350,10 +369,13 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 						if (releases >= 1) umma_commit(wempty_tap(tap));
 						if (releases == 2) umma_commit(wempty_tap(tap));
 					}
-					umma_commit(empty_bar(s));
-					umma_commit(tfull_bar(as));
+					if (!W.dead) {
+						umma_commit(empty_bar(s));
+						umma_commit(tfull_bar(as));
+					}
 				}
 				__syncwarp();
+				W.sync_warp();
 			}
 		}
 	} else {
@@ -364,6 +386,7 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 		const int etid = threadIdx.x - 64;
 		const uint32_t sw = static_cast<uint32_t>(row & 7);
 		const int coff = half * 4;
+		Waiter W(p.status, TC_KERNEL_TRUNK);
 		if (p.pdl) grid_dependency_wait();
 		int it = 0;
 		for (int l = 0; l < p.n_layers; ++l) {
@@ -395,7 +418,7 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 						res[0] = res[1] = res[2] = res[3] = make_uint4(0u, 0u, 0u, 0u);
 					}
 				}
-				mbar_wait(tfull_bar(as), aph, p.error_flag, 5);
+				W.wait(tfull_bar(as), aph, 5);
 				tcgen05_fence_after();
 				uint32_t acc[32];
 				const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
@@ -405,8 +428,9 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 				tmem_ld_wait();
 				tcgen05_fence_before();
 				__syncwarp();
-				if (lane == 0) mbar_arrive(tempty_bar(as));
-				mbar_wait(sfree_bar(ss), sph ^ 1u, p.error_flag, 11);  // staging[ss] consumed by the store of tile it-2
+				W.sync_warp();
+				if (lane == 0 && !W.dead) mbar_arrive(tempty_bar(as));
+				W.wait(sfree_bar(ss), sph ^ 1u, 11);  // staging[ss] consumed by the store of tile it-2
 				float v[32];
 #pragma unroll
 				for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(acc[c]) + bias_reg[c];
@@ -444,7 +468,8 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 				// generic-proxy smem writes -> visible to the TMA (async proxy), then hand the tile over
 				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 				__syncwarp();
-				if (lane == 0) mbar_arrive(sready_bar(ss));
+				W.sync_warp();
+				if (lane == 0 && !W.dead) mbar_arrive(sready_bar(ss));
 			}
 		}
 	}
@@ -497,7 +522,7 @@ cudaError_t trunk_df_tc_prepare(const TrunkArgs &a, TrunkTcLaunch *out) {
 	p.n_layers = a.n_layers;
 	p.act = a.act;
 	p.slope = a.slope;
-	p.pdl = 1;
+	p.pdl = a.cooperative ? 0 : 1;  // a cooperative grid is gang-scheduled: no early (programmatic) start
 	p.bias = a.bias;
 	p.sync_counter = a.sync_counter;
 	p.flags = a.flags;
@@ -554,6 +579,10 @@ cudaError_t trunk_df_tc_prepare(const TrunkArgs &a, TrunkTcLaunch *out) {
 	}
 	std::memcpy(out->maps, &maps, sizeof(maps));
 	std::memcpy(out->params, &p, sizeof(p));
+	// per device and cheap: set at every prepare (plan time), never on the launch path
+	cudaError_t attrErr = cudaFuncSetAttribute(trunk_df_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	    static_cast<int>(kSmemLimit));
+	if (attrErr != cudaSuccess) return attrErr;
 	int dev = 0, sms = 148;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -561,34 +590,35 @@ cudaError_t trunk_df_tc_prepare(const TrunkArgs &a, TrunkTcLaunch *out) {
 	out->grid = p.total_tiles < sms ? p.total_tiles : sms;
 	out->smem_bytes = kFixed + static_cast<uint32_t>(p.stages) * kARegion;
 	out->sync_counter = a.sync_counter;
+	out->cooperative = a.cooperative;
 	return cudaSuccess;
 }
 
-cudaError_t trunk_df_tc_launch(const TrunkTcLaunch &l, int *error_flag, cudaStream_t s) {
-	static bool attr_set[16] = {false};
-	int dev = 0;
-	cudaGetDevice(&dev);
-	if (dev >= 0 && dev < 16 && !attr_set[dev]) {
-		cudaError_t e = cudaFuncSetAttribute(trunk_df_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-		    static_cast<int>(kSmemLimit));
-		if (e != cudaSuccess) return e;
-		attr_set[dev] = true;
-	}
+cudaError_t trunk_df_tc_launch(const TrunkTcLaunch &l, TcStatus *status, cudaStream_t s) {
 	TrunkMaps maps;
 	TrunkParams p;
 	std::memcpy(&maps, l.maps, sizeof(maps));
 	std::memcpy(&p, l.params, sizeof(p));
-	p.error_flag = error_flag;
+	p.status = status;
 	cudaLaunchConfig_t cfg{};
 	cfg.gridDim = dim3(l.grid);
 	cfg.blockDim = dim3(kThreadsT);
 	cfg.dynamicSmemBytes = l.smem_bytes;
 	cfg.stream = s;
-	cudaLaunchAttribute attr[1];
-	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cudaLaunchAttribute attr[2];
+	int n = 0;
+	if (p.pdl) {
+		attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+		attr[n].val.programmaticStreamSerializationAllowed = 1;
+		++n;
+	}
+	if (l.cooperative) {
+		attr[n].id = cudaLaunchAttributeCooperative;
+		attr[n].val.cooperative = 1;
+		++n;
+	}
 	cfg.attrs = attr;
-	cfg.numAttrs = p.pdl ? 1 : 0;
+	cfg.numAttrs = n;
 	return cudaLaunchKernelEx(&cfg, trunk_df_tc_kernel, maps, p);
 }
 

@@ -15,7 +15,7 @@ import numpy as np
 from .runtime import JoshUpscaleError, _check, load_library
 
 ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
-IMPL_SIMT, IMPL_TCGEN05, IMPL_TCGEN05_2CTA = 0, 1, 2
+IMPL_SIMT, IMPL_TCGEN05 = 0, 1
 
 
 class DeviceArray:
@@ -100,7 +100,7 @@ def conv(x: np.ndarray, kernel: np.ndarray, scale=None, bias=None, residual=None
     xin = np.zeros((b, h, w, cin_stride), np.float16)
     xin[..., :cin] = x
     d_x = to_device(xin)
-    if impl in (IMPL_TCGEN05, IMPL_TCGEN05_2CTA):
+    if impl == IMPL_TCGEN05:
         cin_p = cin_stride
     d_w = to_device(pack_conv_weights(kernel, scale, cin_p, impl))
     d_b = to_device(np.asarray(bias, np.float32)) if bias is not None else None

@@ -62,6 +62,7 @@ SYMBOLS = {
     "ju_last_error": (C.c_char_p, []),
     "ju_set_log_sink": (None, [_VP, _VP]),
     "ju_reset_state": (_I, [_VP]),
+    "ju_debug_inject_stall": (_I, [_VP, _I]),
     "ju_read_tensor": (_I, [_VP, C.c_char_p, _VP, _U64, C.POINTER(JuTensorDesc)]),
     "ju_write_state": (_I, [_VP, C.c_char_p, _VP, _U64]),
     "ju_profile_ops": (_I, [_VP, _I, C.POINTER(JuOpTime), _I, C.POINTER(_I)]),
@@ -217,6 +218,10 @@ class Runtime:
     # ---- state / debug --------------------------------------------------
     def reset_state(self) -> None:
         _check(self._lib.ju_reset_state(self._h))
+
+    def inject_stall(self, kernel_id: int = 1) -> None:
+        """Test hook: the next frame's kernel `kernel_id` (1 = persistent trunk) stalls."""
+        _check(self._lib.ju_debug_inject_stall(self._h, kernel_id))
 
     def read_tensor(self, name: str) -> np.ndarray:
         desc = JuTensorDesc()

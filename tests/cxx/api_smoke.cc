@@ -41,6 +41,20 @@ int main(int argc, char **argv) {
 		if (msg.find("model.jup") == std::string::npos) return 4;
 	}
 
+	// graphics interop on a machine without a GL context (this box is headless): both entry points
+	// must fail with an exception, like the reference's, never crash or return a dummy
+	try {
+		std::unique_ptr<core::GraphicsResourceImage> tex(core::getGLImage(1, core::GraphicsResourceImageType::INPUT));
+		std::cout << "getGLImage succeeded: a GL context is current\n";
+	} catch (...) {
+		std::cout << "getGLImage: " << core::getExceptionString() << "\n";
+	}
+	try {
+		std::cout << "GL device " << core::getGLDeviceIndex() << "\n";
+	} catch (...) {
+		std::cout << "getGLDeviceIndex: " << core::getExceptionString() << "\n";
+	}
+
 	std::unique_ptr<core::Runtime> runtime;
 	try {
 		runtime.reset(core::createRuntime(0, argv[1]));

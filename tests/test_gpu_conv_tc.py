@@ -172,18 +172,16 @@ def test_conv_tc_fused_maxpool(b, h, w, cin, cout):
     np.testing.assert_array_equal(pooled.view(np.uint16), want.view(np.uint16))
 
 
-@pytest.mark.parametrize("sync", ["barrier", "dataflow"])
 @pytest.mark.parametrize("preset,batch", [("small", 1), ("small", 3), ("psp_fast", 1), ("psp_fast", 2)])
-def test_persistent_trunk_bit_identical_to_per_layer_launches(tmp_path, preset, batch, sync):
-    """The persistent ResBlock trunk (one launch; grid barrier or per-tile dataflow flags between
-    layers) performs the same arithmetic as one conv_tc launch per layer: bit-identical outputs."""
+def test_persistent_trunk_bit_identical_to_per_layer_launches(tmp_path, preset, batch):
+    """The persistent ResBlock trunk (one launch, per-wave dataflow counters between layers)
+    performs the same arithmetic as one conv_tc launch per layer: bit-identical outputs."""
     cfg, w, path = make_model(tmp_path, preset)
     nframes = 6
     frames = [synthetic.frames(cfg.frame_height, cfg.frame_width, nframes, stream_id=s) for s in range(batch)]
     outs = {}
     for fused in ("1", "0"):
         os.environ["JU_FUSED_TRUNK"] = fused
-        os.environ["JU_TRUNK_SYNC"] = "1" if sync == "dataflow" else "0"
         try:
             with jrt.Runtime(path, 0, batch) as rt:
                 res = []
@@ -192,7 +190,6 @@ def test_persistent_trunk_bit_identical_to_per_layer_launches(tmp_path, preset, 
                 outs[fused] = np.stack(res)
         finally:
             os.environ.pop("JU_FUSED_TRUNK", None)
-            os.environ.pop("JU_TRUNK_SYNC", None)
     np.testing.assert_array_equal(outs["1"], outs["0"])
 
 
@@ -202,19 +199,15 @@ def test_dataflow_trunk_race_stress(tmp_path):
     for preset, nframes in (("psp_quality", 24), ("psp_fast", 40)):
         cfg, w, path = make_model(tmp_path, preset)
         frames = synthetic.frames(270, 480, 4)
-        os.environ["JU_TRUNK_SYNC"] = "1"
-        try:
-            with jrt.Runtime(path) as rt:
-                first = None
-                for rep in range(nframes // 4):
-                    rt.reset_state()
-                    got = np.stack([rt.process(f) for f in frames])
-                    if first is None:
-                        first = got
-                    else:
-                        np.testing.assert_array_equal(got, first)
-        finally:
-            os.environ.pop("JU_TRUNK_SYNC", None)
+        with jrt.Runtime(path) as rt:
+            first = None
+            for rep in range(nframes // 4):
+                rt.reset_state()
+                got = np.stack([rt.process(f) for f in frames])
+                if first is None:
+                    first = got
+                else:
+                    np.testing.assert_array_equal(got, first)
         os.environ["JU_FUSED_TRUNK"] = "0"
         try:
             with jrt.Runtime(path) as rt:

@@ -174,10 +174,18 @@ def test_errors_leave_state_untouched(tmp_path):
         np.testing.assert_array_equal(rt.process(frames[0]), want[0])
         with pytest.raises(jrt.JoshUpscaleError, match="size"):
             rt.process(np.zeros((h + 1, wd, 4), np.uint8))
-        bad = jrt.JuImage(1, jrt.LOC_GRAPHICS_RESOURCE, 0, wd, h)
+        bad = jrt.JuImage(1, 7, 0, wd, h)
         good = jrt._image(np.empty(rt.out_shape, np.uint8), 0, 0)
-        with pytest.raises(jrt.JoshUpscaleError, match="GRAPHICS_RESOURCE"):
+        with pytest.raises(jrt.JoshUpscaleError, match="unknown image location"):
             rt.process_images([bad], [good])
+        # CUDA images: pointer / stride must be 4-byte aligned and at least one row wide
+        d_in = jk.to_device(frames[1])
+        d_out = jk.DeviceArray((4 * h, 4 * wd, 4), np.uint8)
+        ok_in = jrt.JuImage(d_in.ptr, jrt.LOC_CUDA, wd * 4, wd, h)
+        for bad_out in (jrt.JuImage(d_out.ptr + 2, jrt.LOC_CUDA, wd * 16, 4 * wd, 4 * h),
+                        jrt.JuImage(d_out.ptr, jrt.LOC_CUDA, wd * 16 - 4, 4 * wd, 4 * h)):
+            with pytest.raises(jrt.JoshUpscaleError, match="aligned|stride"):
+                rt.process_images([ok_in], [bad_out])
         np.testing.assert_array_equal(rt.process(frames[1]), want[1])
 
 
