@@ -36,8 +36,8 @@ int envInt(const char *name, int fallback) {
 // kernel has inter-CTA dependencies (trunk_df_tc.cu): all of its CTAs must be resident together,
 // which holds when a frame has the device to itself (grid <= SM count, one CTA per SM) but not
 // when two engines driven from two threads interleave their 227 KB-per-CTA kernels.  The trunks
-// fill every SM anyway, so nothing is lost by taking turns.  (Other processes sharing the GPU
-// through MPS are covered by JU_TRUNK_COOP=1, a cooperative launch.)
+// fill every SM anyway, so nothing is lost by taking turns.  Other processes sharing the GPU
+// (MPS) are covered by the cooperative launch of the persistent kernels (JU_TRUNK_COOP, default 1).
 std::mutex &deviceMutex(int device) {
 	static std::mutex mutexes[64];
 	return mutexes[device >= 0 && device < 64 ? device : 63];
@@ -67,8 +67,11 @@ Engine::Engine(const ModelFile &model, int device, int batch)
 	m_TcOpt.pdl = envInt("JU_TC_PDL", m_TcOpt.pdl);
 	m_TcOpt.dual = envInt("JU_TC_DUAL", m_TcOpt.dual);
 	m_UseGraph = envInt("JU_NO_GRAPH", 0) == 0;
-	m_TrunkCooperative = envInt("JU_TRUNK_COOP", 0) != 0;
+	// cooperative launch of the persistent kernels (co-residency guaranteed by the driver, also
+	// against other processes); measured free: 171.8 vs 171.9 us for the psp_fast trunk
+	m_TrunkCooperative = envInt("JU_TRUNK_COOP", 1) != 0;
 	m_WaitTimeoutMs = envInt("JU_WAIT_TIMEOUT_MS", 0);
+	m_CopyThreads = envInt("JU_COPY_THREADS", 4);  // 0 = let the driver stage pageable images
 	JU_CUDA(cudaStreamCreateWithFlags(&m_Stream, cudaStreamNonBlocking));
 	JU_CUDA(cudaStreamCreateWithFlags(&m_CopyStream, cudaStreamNonBlocking));
 	try {
@@ -833,7 +836,9 @@ void Engine::bindImages(int n, const ju_image *inputs, const ju_image *outputs) 
 	FrameIO *io = m_IoHost.as<FrameIO>();
 	m_LastOutputs.assign(outputs, outputs + n);
 	m_OutputNeedsCopy.assign(n, false);
+	m_OutputPooled.assign(n, false);
 	m_OutputArrays.assign(n, nullptr);
+	std::vector<int> pooledInputs;
 	// GRAPHICS_RESOURCE images (reference core/src/cuda_convert.cc.cu:381-397, 420-436): ptr is a
 	// registered cudaGraphicsResource_t (getGLImage / getD3D11Image); it is mapped for the duration
 	// of the frame and its array copied to / from the staging buffers on the frame's stream
@@ -875,7 +880,22 @@ void Engine::bindImages(int n, const ju_image *inputs, const ju_image *outputs) 
 		if (in.location == JU_LOC_CPU) {
 			if (absStride(in.stride) < inRow) throw std::invalid_argument("input stride smaller than a row");
 			const auto *p = static_cast<const std::uint8_t *>(in.ptr);
-			if (in.stride == static_cast<std::int64_t>(inRow)) {
+			if (m_CopyThreads > 0 && isPageable(p)) {
+				// pageable caller memory: gather the rows into the engine's pinned buffer on the copy
+				// pool (all streams in parallel), then one asynchronous host-to-device copy below
+				ensureHostStaging();
+				CopyJob job;
+				job.dst = m_InPinned.as<std::uint8_t>() + s * H * inRow;
+				job.src = p;
+				job.dstStride = static_cast<std::ptrdiff_t>(inRow);
+				job.srcStride = static_cast<std::ptrdiff_t>(in.stride);  // image row i lives at ptr + i * stride
+				job.rowBytes = inRow;
+				job.rows = H;
+				m_Pool->submit(job);
+				pooledInputs.push_back(s);
+				f.in = inStage;
+				f.in_stride = static_cast<long long>(inRow);
+			} else if (in.stride == static_cast<std::int64_t>(inRow)) {
 				JU_CUDA(cudaMemcpyAsync(inStage, p, inRow * H, cudaMemcpyHostToDevice, m_Stream));
 				f.in = inStage;
 				f.in_stride = static_cast<long long>(inRow);
@@ -909,7 +929,14 @@ void Engine::bindImages(int n, const ju_image *inputs, const ju_image *outputs) 
 		if (out.location == JU_LOC_CPU) {
 			if (absStride(out.stride) < outRow) throw std::invalid_argument("output stride smaller than a row");
 			m_OutputNeedsCopy[s] = true;
-			if (out.stride >= 0) {
+			if (m_CopyThreads > 0 && isPageable(out.ptr)) {
+				// pageable caller memory: device -> pinned (asynchronous, band by band), then the copy
+				// pool scatters the rows into the caller's image (process())
+				ensureHostStaging();
+				m_OutputPooled[s] = true;
+				f.out = outStage;
+				f.out_stride = static_cast<long long>(outRow);
+			} else if (out.stride >= 0) {
 				f.out = outStage;
 				f.out_stride = static_cast<long long>(outRow);
 			} else {
@@ -929,6 +956,13 @@ void Engine::bindImages(int n, const ju_image *inputs, const ju_image *outputs) 
 			f.out_stride = static_cast<long long>(outRow);
 		} else {
 			throw std::invalid_argument("unknown image location");
+		}
+	}
+	if (!pooledInputs.empty()) {
+		m_Pool->wait();
+		for (int s : pooledInputs) {
+			JU_CUDA(cudaMemcpyAsync(m_InStage.as<std::uint8_t>() + s * H * inRow, m_InPinned.as<std::uint8_t>() + s * H * inRow,
+			    H * inRow, cudaMemcpyHostToDevice, m_Stream));
 		}
 	}
 	// the device-side address table only changes when the caller's pointers do: host images always
@@ -967,6 +1001,31 @@ void Engine::recoverFromStall() {
 	}
 }
 
+// cudaPointerGetAttributes: ordinary heap memory is "unregistered"; pinned / registered host memory
+// can be the target of a truly asynchronous copy and keeps the direct path
+bool Engine::isPageable(const void *ptr) {
+	cudaPointerAttributes attr{};
+	const cudaError_t e = cudaPointerGetAttributes(&attr, ptr);
+	if (e != cudaSuccess) {
+		(void) cudaGetLastError();
+		return true;
+	}
+	return attr.type == cudaMemoryTypeUnregistered;
+}
+
+void Engine::ensureHostStaging() {
+	if (m_Pool) return;
+	const std::size_t H = m_Spec.frameH, W = m_Spec.frameW;
+	m_InPinned = PinnedBuffer(static_cast<std::size_t>(m_Batch) * H * W * 4);
+	m_OutPinned = PinnedBuffer(static_cast<std::size_t>(m_Batch) * 16 * H * W * 4);
+	m_Pool = std::make_unique<HostCopyPool>(m_CopyThreads);
+}
+
+void CUDART_CB Engine::bandArrived(void *user) {
+	auto *band = static_cast<BandCopy *>(user);
+	band->pool->submit(band->job);
+}
+
 void Engine::unmapResources() {
 	if (m_MappedResources.empty()) return;
 	std::vector<cudaGraphicsResource_t> res;
@@ -992,7 +1051,8 @@ void Engine::process(int n, const ju_image *inputs, const ju_image *outputs) {
 		// Device-to-host copies of staged images run on a second stream, one group of streams at a
 		// time as soon as the frame graph has recorded that group's completion event: with several
 		// sub-batches the copies of the first streams overlap the trunk of the later ones.
-		bool copied = false;
+		bool copied = false, pooled = false;
+		m_BandCopies.clear();
 		for (const Region &r : m_Regions[variant]) {
 			const int b0 = r.b0, b1 = std::min(n, r.b0 + r.nb);
 			bool any = false;
@@ -1005,7 +1065,22 @@ void Engine::process(int n, const ju_image *inputs, const ju_image *outputs) {
 				const ju_image &out = outputs[s];
 				const std::uint8_t *stage = m_OutStage.as<std::uint8_t>() + s * 4 * H * outRow;
 				auto *p = static_cast<std::uint8_t *>(out.ptr);
-				if (out.stride == static_cast<std::int64_t>(outRow)) {
+				if (m_OutputPooled[s]) {
+					std::uint8_t *pinned = m_OutPinned.as<std::uint8_t>() + s * 4 * H * outRow + r.row0 * outRow;
+					JU_CUDA(cudaMemcpyAsync(pinned, stage + r.row0 * outRow, rows * outRow, cudaMemcpyDeviceToHost, m_CopyStream));
+					auto band = std::make_unique<BandCopy>();
+					band->pool = m_Pool.get();
+					band->job.dst = p + static_cast<std::ptrdiff_t>(r.row0) * static_cast<std::ptrdiff_t>(out.stride);
+					band->job.src = pinned;
+					band->job.dstStride = static_cast<std::ptrdiff_t>(out.stride);
+					band->job.srcStride = static_cast<std::ptrdiff_t>(outRow);
+					band->job.rowBytes = outRow;
+					band->job.rows = rows;
+					// runs on the copy stream right after the band has arrived in pinned memory
+					JU_CUDA(cudaLaunchHostFunc(m_CopyStream, &Engine::bandArrived, band.get()));
+					m_BandCopies.push_back(std::move(band));
+					pooled = true;
+				} else if (out.stride == static_cast<std::int64_t>(outRow)) {
 					// dense image: one linear copy
 					JU_CUDA(cudaMemcpyAsync(p + r.row0 * outRow, stage + r.row0 * outRow, rows * outRow,
 					    cudaMemcpyDeviceToHost, m_CopyStream));
@@ -1033,6 +1108,7 @@ void Engine::process(int n, const ju_image *inputs, const ju_image *outputs) {
 		unmapResources();
 		JU_CUDA(cudaStreamSynchronize(m_Stream));
 		if (copied) JU_CUDA(cudaStreamSynchronize(m_CopyStream));
+		if (pooled) m_Pool->wait();  // every band's host function has run: all rows are queued or done
 		const int stall = *static_cast<volatile int *>(m_StatusHost.as<int>());
 		if (stall != 0) {
 			recoverFromStall();
@@ -1049,6 +1125,7 @@ void Engine::process(int n, const ju_image *inputs, const ju_image *outputs) {
 		}
 		cudaStreamSynchronize(m_Stream);
 		cudaStreamSynchronize(m_CopyStream);
+		if (m_Pool) m_Pool->wait();
 		throw;
 	}
 	m_Parity ^= 1;

@@ -19,6 +19,7 @@
 
 #include "../kernels/kernels.h"
 #include "common.h"
+#include "copy_pool.h"
 #include "joshupscale_c.h"
 #include "model.h"
 
@@ -111,6 +112,9 @@ private:
 	    std::vector<std::uint64_t> dims, std::size_t bytes, bool writable);
 	void bindImages(int n, const ju_image *inputs, const ju_image *outputs);
 	void unmapResources();
+	static bool isPageable(const void *ptr);
+	void ensureHostStaging();
+	static void CUDART_CB bandArrived(void *user);
 	void uploadStatus(int inject);
 	void recoverFromStall();
 
@@ -139,6 +143,16 @@ private:
 	DeviceBuffer m_InStage, m_OutStage;
 	std::vector<ju_image> m_LastOutputs;
 	std::vector<bool> m_OutputNeedsCopy;
+	std::vector<bool> m_OutputPooled;  // pageable output: device -> m_OutPinned -> copy pool -> caller
+	// pageable host images (the plugins' case): engine-owned pinned staging + a multi-threaded memcpy
+	struct BandCopy {
+		HostCopyPool *pool;
+		CopyJob job;
+	};
+	int m_CopyThreads = 4;
+	std::unique_ptr<HostCopyPool> m_Pool;
+	PinnedBuffer m_InPinned, m_OutPinned;
+	std::vector<std::unique_ptr<BandCopy>> m_BandCopies;  // alive until the frame's streams are synchronised
 	std::vector<cudaArray_t> m_OutputArrays;                 // per stream: mapped output array or null
 	std::vector<cudaGraphicsResource_t> m_MappedResources;  // mapped for the frame in flight
 
