@@ -272,8 +272,8 @@ void Engine::allocate() {
 	const ModelSpec &s = m_Spec;
 	const std::uint64_t B = m_Batch, H = s.frameH, W = s.frameW, PH = s.padH, PW = s.padW;
 	m_Status = DeviceBuffer(sizeof(TcStatus));
-	m_StatusHost = PinnedBuffer(sizeof(int));
-	*m_StatusHost.as<int>() = 0;
+	m_StatusHost = PinnedBuffer(2 * sizeof(int));
+	m_StatusHost.as<int>()[0] = m_StatusHost.as<int>()[1] = 0;
 	uploadStatus(0);
 	m_Brightness = DeviceBuffer(sizeof(float) * B);
 	m_IoHost = PinnedBuffer(sizeof(FrameIO) * B);
@@ -439,7 +439,12 @@ void Engine::buildPlan(int parity, int variant) {
 		x = out;
 		xs = os;
 	};
-	if (s.flowArch == 0) {
+	bool flowDone = false;
+	if (s.flowArch == 0 && flowNetFusable()) {
+		// the whole autoencoder incl. the head as one persistent dataflow kernel (flow_df_tc.cu)
+		emitFlowNet(plan, flowNext, activation);
+		flowDone = true;
+	} else if (s.flowArch == 0) {
 		int n = static_cast<int>(s.flowFilters.size()) / 2;
 		for (int i = 0; i < 2 * n; ++i) {
 			std::string p = "flow/block_" + std::to_string(i + 1);
@@ -511,8 +516,10 @@ void Engine::buildPlan(int parity, int variant) {
 			}
 		}
 	}
-	if (h != PH || w != PW) throw ModelException("flow net does not return to input resolution");
-	plan.push_back(convOp(layer("flow/conv_2"), x, xs, nullptr, m_FlowHead.get(), 32, PH, PW, true));
+	if (!flowDone) {
+		if (h != PH || w != PW) throw ModelException("flow net does not return to input resolution");
+		plan.push_back(convOp(layer("flow/conv_2"), x, xs, nullptr, m_FlowHead.get(), 32, PH, PW, true));
+	}
 
 	// ---- warp + space-to-depth + concat --------------------------------
 	{
@@ -602,6 +609,159 @@ void Engine::buildPlan(int parity, int variant) {
 	}
 	if (m_FilterOn) plan.push_back(filterOp(io, preGenNext, bright, 0, B));
 	plan.push_back(chunkDoneOp(0, B, 0, 4 * H));
+}
+
+// get_flow_autoencoder (models.py:334-481) can run as the persistent flow kernel when every
+// convolution has a tcgen05 kernel with the TMA-store epilogue (Cout = 32 or a multiple of 64)
+// and every MaxPool sees even sizes.
+bool Engine::flowNetFusable() const {
+	const ModelSpec &s = m_Spec;
+	// Opt-in (JU_FUSED_FLOW=1): measured SLOWER than one launch per layer on B200 - 222 vs 141 us at
+	// batch 1, 1536 vs 1126 us at batch 16 (profiles/r02_flow_df_probe.txt) - because a layer
+	// boundary inside the kernel (bulk-store completion, GPU-scope release, acquire, cold pipeline)
+	// costs ~6 us against ~5 us for a kernel boundary in the captured graph; see flow_df_tc.cu.
+	if (m_ConvImpl != 1 || !m_TcOpt.tma_epilogue || envInt("JU_FUSED_FLOW", 0) == 0 || envInt("JU_FUSED_POOL", 1) == 0) {
+		return false;
+	}
+	const int n = static_cast<int>(s.flowFilters.size()) / 2;
+	int h = s.padH, w = s.padW;
+	auto usable = [&](const std::string &name) {
+		auto it = m_LayerByName.find(name);
+		return it != m_LayerByName.end() && it->second->wTc.get() && it->second->ksize == 3 &&
+		       (it->second->cout == 32 || it->second->cout % 64 == 0);
+	};
+	for (int i = 0; i < 2 * n; ++i) {
+		const std::string p = "flow/block_" + std::to_string(i + 1);
+		if (!usable(p + "/conv_1") || !usable(p + "/conv_2")) return false;
+		if (i < n) {
+			if ((h | w) & 1) return false;
+			h /= 2;
+			w /= 2;
+		} else {
+			h *= 2;
+			w *= 2;
+		}
+	}
+	if (s.flowFilters.size() % 2 && !usable("flow/conv_1")) return false;
+	if (2 * n + n + 2 > flow_df_max_layers()) return false;
+	return usable("flow/conv_2") && h == s.padH && w == s.padW;
+}
+
+// ConvArgs of layer L on the tcgen05 path (what convOp passes to conv_tc_prepare)
+ConvArgs Engine::tcConvArgs(ConvLayer *L, const __half *in, int cinStride, void *out, int coutStride, int h, int w,
+    bool outF32, bool pool) const {
+	ConvArgs a{};
+	a.in = in;
+	a.weights = L->wTc.get();
+	a.bias = L->bias.as<float>();
+	a.residual = nullptr;
+	a.out = out;
+	a.batch = m_Batch;
+	a.h = h;
+	a.w = w;
+	a.cin_stride = cinStride;
+	a.cin = pad64(L->cinReal);
+	a.cin_live = L->cinReal;
+	a.cout = L->cout;
+	a.cout_stride = coutStride;
+	a.ksize = L->ksize;
+	a.act = L->act;
+	a.slope = L->slope;
+	a.out_f32 = outF32 ? 1 : 0;
+	a.shuffle2 = 0;
+	a.pool = pool ? 1 : 0;
+	if (a.cin > cinStride) throw ModelException("channel stride too small for " + L->name);
+	return a;
+}
+
+void Engine::emitFlowNet(std::vector<Op> &plan, const __half *input, const std::function<__half *(std::size_t)> &activation) {
+	const ModelSpec &s = m_Spec;
+	const int B = m_Batch, PH = s.padH, PW = s.padW;
+	const int n = static_cast<int>(s.flowFilters.size()) / 2;
+	std::vector<FlowLayerSpec> specs;
+	double flops = 0, bytes = 0;
+	const __half *x = input;
+	int xs = m_FlowCStride, h = PH, w = PW;
+	auto addConv = [&](const std::string &name, void *out, int os, bool outF32, bool pool) {
+		ConvLayer *L = m_LayerByName.at(name);
+		FlowLayerSpec spec{};
+		spec.kind = 0;
+		spec.conv = tcConvArgs(L, x, xs, out, os, h, w, outF32, pool);
+		specs.push_back(spec);
+		flops += 2.0 * B * h * w * 9.0 * L->cinReal * L->cout;
+		bytes += static_cast<double>(B) * h * w * (L->cinReal * 2.0 + L->cout * (outF32 ? 4.0 : 2.0) * (pool ? 0.25 : 1.0));
+	};
+	auto bytesOf = [&](int hh, int ww, int c) { return static_cast<std::size_t>(B) * hh * ww * c * sizeof(__half); };
+	for (int i = 0; i < 2 * n; ++i) {
+		const std::string p = "flow/block_" + std::to_string(i + 1);
+		const int os1 = pad64(m_LayerByName.at(p + "/conv_1")->cout), os2 = pad64(m_LayerByName.at(p + "/conv_2")->cout);
+		__half *o1 = activation(bytesOf(h, w, os1));
+		addConv(p + "/conv_1", o1, os1, false, false);
+		x = o1;
+		xs = os1;
+		if (i < n) {
+			// conv_2 + BN + act + MaxPool2D(2) (models.py:386-409): pooled in the epilogue
+			__half *pooled = activation(bytesOf(h / 2, w / 2, os2));
+			addConv(p + "/conv_2", pooled, os2, false, true);
+			x = pooled;
+			h /= 2;
+			w /= 2;
+		} else {
+			// conv_2, then UpscaleLayer(bilinear, 2) (models.py:441-446) as an element-wise layer
+			__half *o2 = activation(bytesOf(h, w, os2));
+			addConv(p + "/conv_2", o2, os2, false, false);
+			__half *up = activation(bytesOf(2 * h, 2 * w, os2));
+			FlowLayerSpec spec{};
+			spec.kind = 1;
+			spec.up_src = o2;
+			spec.up_dst = up;
+			spec.up_h = h;
+			spec.up_w = w;
+			spec.up_c = os2;
+			specs.push_back(spec);
+			bytes += static_cast<double>(B) * h * w * s.flowFilters[i] * 2.0 * 5.0;
+			x = up;
+			h *= 2;
+			w *= 2;
+		}
+		xs = os2;
+	}
+	if (s.flowFilters.size() % 2) {
+		const int os = pad64(m_LayerByName.at("flow/conv_1")->cout);
+		__half *o = activation(bytesOf(h, w, os));
+		addConv("flow/conv_1", o, os, false, false);
+		x = o;
+		xs = os;
+	}
+	addConv("flow/conv_2", m_FlowHead.get(), 32, true, false);
+
+	const int nLayers = static_cast<int>(specs.size());
+	if (!m_FlowCounters.get()) {
+		m_FlowCounters = DeviceBuffer(flow_df_counter_words(nLayers, B) * sizeof(unsigned int));
+		m_FlowSync = DeviceBuffer(2 * sizeof(unsigned int));
+	}
+	// JU_FLOW_SUBBATCH: streams per pass over all layers (-1: see below, 0: the whole batch).  A pass
+	// costs ~3 us of pipeline fill / drain per layer and CTA, a whole-batch pass streams every
+	// activation through HBM once the batch no longer fits the L2
+	int chunk = envInt("JU_FLOW_SUBBATCH", -1);
+	if (chunk < 0) chunk = B <= 4 ? B : 4;
+	if (chunk == 0 || chunk > B) chunk = B;
+	FlowDfLaunch launch{};
+	// JU_FLOW_DEBUG_LAYERS=n: run only the first n layers (bisecting a stalled pipeline; the frame is wrong)
+	const int debugLayers = envInt("JU_FLOW_DEBUG_LAYERS", 0);
+	checkCuda(flow_df_tc_prepare(specs.data(), debugLayers > 0 && debugLayers < nLayers ? debugLayers : nLayers, m_TcOpt, B, chunk,
+	              m_FlowCounters.as<unsigned int>(), m_FlowSync.as<unsigned int>(), m_TrunkCooperative ? 1 : 0, &launch),
+	    "flow_df_tc_prepare");
+	TcStatus *status = m_Status.as<TcStatus>();
+	Op op;
+	op.name = "flow/*(persistent)";
+	op.tensorBound = true;
+	op.layers = nLayers;
+	op.flops = flops;
+	op.bytes = bytes;
+	op.run = [launch, status](cudaStream_t st) { return flow_df_tc_launch(launch, status, st); };
+	plan.push_back(std::move(op));
+	++m_TcOps;
 }
 
 // A stack of `nBlocks` ResBlocks (3x3 64->64 conv + BN + act, conv + BN + shortcut + act;
@@ -993,11 +1153,15 @@ void Engine::injectStall(int kernelId) {
 // Re-arm everything the aborted frame may have left half-way - the status block and the
 // never-reset dataflow counters of the persistent trunks - so that the next frame starts clean.
 void Engine::recoverFromStall() {
-	*m_StatusHost.as<int>() = 0;
+	m_StatusHost.as<int>()[0] = m_StatusHost.as<int>()[1] = 0;
 	uploadStatus(0);
 	for (TrunkState *ts : {&m_GenTrunk, &m_FlowTrunk}) {
 		if (ts->counter.get()) JU_CUDA(cudaMemset(ts->counter.get(), 0, ts->counter.bytes()));
 		if (ts->flags.get()) JU_CUDA(cudaMemset(ts->flags.get(), 0, ts->flags.bytes()));
+	}
+	if (m_FlowCounters.get()) {
+		JU_CUDA(cudaMemset(m_FlowCounters.get(), 0, m_FlowCounters.bytes()));
+		JU_CUDA(cudaMemset(m_FlowSync.get(), 0, m_FlowSync.bytes()));
 	}
 }
 
@@ -1111,9 +1275,17 @@ void Engine::process(int n, const ju_image *inputs, const ju_image *outputs) {
 		if (pooled) m_Pool->wait();  // every band's host function has run: all rows are queued or done
 		const int stall = *static_cast<volatile int *>(m_StatusHost.as<int>());
 		if (stall != 0) {
+			const int where = static_cast<volatile int *>(m_StatusHost.as<int>())[1];
+			TcStatus snapshot{};
+			cudaMemcpy(&snapshot, m_Status.get(), sizeof(snapshot), cudaMemcpyDeviceToHost);
+			std::string pending;
+			for (int c = 0; c < 32; ++c) {
+				if (snapshot.pending & (1u << c)) pending += (pending.empty() ? "" : ",") + std::to_string(c);
+			}
 			recoverFromStall();
 			throw KernelStallException(std::string("frame aborted: ") + tc_kernel_name(stall >> 8) +
-			                           " pipeline wait " + std::to_string(stall & 0xff) + " expired");
+			                           " pipeline wait " + std::to_string(stall & 0xff) + " expired (layer " +
+			                           std::to_string(where >> 16) + ", CTA " + std::to_string(where & 0xffff) + "; blocked waits: " + pending + ")");
 		}
 	} catch (...) {
 		// a failed frame leaves the ping-pong index unchanged (the reference flips only after the

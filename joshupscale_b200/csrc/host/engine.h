@@ -104,6 +104,10 @@ private:
 	    __half *t1, __half *t2, int cstride, int H, int W, ConvLayer *lead, const __half *leadIn,
 	    const std::function<void(const __half *, int, int, bool)> &afterChunk);
 	void emitTail(std::vector<Op> &plan, int parity, const __half *trunkOut, int gs, int b0, int nb);
+	bool flowNetFusable() const;
+	ConvArgs tcConvArgs(ConvLayer *layer, const __half *in, int cinStride, void *out, int coutStride, int h, int w,
+	    bool outF32, bool pool) const;
+	void emitFlowNet(std::vector<Op> &plan, const __half *input, const std::function<__half *(std::size_t)> &activation);
 	Op chunkDoneOp(int b0, int nb, int row0, int row1);
 	Op convOp(ConvLayer *layer, const __half *in, int cinStride, const __half *residual, void *out,
 	    int coutStride, int h, int w, bool outF32, bool pool = false);
@@ -138,6 +142,7 @@ private:
 	int m_WaitTimeoutMs = 0;
 	DeviceBuffer m_Brightness;
 	TrunkState m_GenTrunk, m_FlowTrunk;
+	DeviceBuffer m_FlowCounters, m_FlowSync;  // persistent flow kernel: row counters, {done, epoch}
 	int m_TcOps = 0;
 	std::set<std::string> m_WarnedSimt;
 	DeviceBuffer m_InStage, m_OutStage;

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <memory>
 
 namespace ju {
 
@@ -31,8 +32,10 @@ struct TcStatus {
 	int code;         // 0 = ok
 	int timeout_ms;   // 0 = default (4 s)
 	int inject;       // fault injection (tests): id of the kernel whose pipeline stalls on purpose
+	int where;        // (layer << 16) | CTA of the wait that expired (persistent kernels)
+	int *host_code;   // mapped pinned host copy of {code, where} (may be null)
+	unsigned int pending;  // bit c set: some thread was blocked in wait c when the frame was aborted
 	int pad;
-	int *host_code;   // mapped pinned host copy of `code` (may be null)
 };
 enum TcKernelId : int { TC_KERNEL_TRUNK = 1, TC_KERNEL_CONV = 2, TC_KERNEL_TAIL = 3, TC_KERNEL_FLOW = 4 };
 const char *tc_kernel_name(int id);
@@ -95,6 +98,7 @@ bool conv_tc_supported(const ConvArgs &a);
 // dependent launch; dual: two alternating producer / issuer pipelines where the layer allows.
 struct ConvTcOptions {
 	int variant, tma_epilogue, pdl, dual;
+	unsigned int smem_limit;  // shared-memory budget of one layer; 0 = everything a CTA may have (227 KB)
 };
 // process-wide defaults (changed by ju_set_option); engines copy them at creation
 ConvTcOptions &conv_tc_default_options();
@@ -169,6 +173,30 @@ cudaError_t trunk_df_tc_prepare(const TrunkArgs &a, TrunkTcLaunch *out);
 cudaError_t trunk_df_tc_launch(const TrunkTcLaunch &l, TcStatus *status, cudaStream_t s);
 // index (0 or 2) of the buffer holding the trunk output after n_layers
 inline int trunk_output_buffer(int n_layers) { return ((n_layers / 2) & 1) ? 2 : 0; }
+
+// ---- persistent flow net (flow_df_tc.cu): all layers of the flow autoencoder in one launch ----
+struct FlowLayerSpec {
+	int kind;                  // 0 = 3x3 convolution (ConvArgs as for conv_tc_prepare), 1 = legacy bilinear x2
+	ConvArgs conv;
+	const __half *up_src;      // kind 1: [batch, up_h, up_w, up_c] -> up_dst [batch, 2 up_h, 2 up_w, up_c]
+	__half *up_dst;
+	int up_h, up_w, up_c;
+};
+struct FlowDfLaunch {
+	std::shared_ptr<const void> table;  // host copy of the layer table, passed by value as a kernel parameter
+	int n_layers, batch, chunk;
+	int grid;
+	unsigned int smem_bytes;
+	unsigned int *counters, *sync;
+	int cooperative;
+};
+int flow_df_max_layers();
+size_t flow_df_counter_words(int n_layers, int batch);    // zero-initialised row counters
+// sync: two zeroed words (finished-CTA counter, launch epoch); chunk: streams per pass over all
+// layers.  Fails (cudaErrorInvalidValue) when a layer cannot run with the TMA-store epilogue.
+cudaError_t flow_df_tc_prepare(const FlowLayerSpec *specs, int n_layers, const ConvTcOptions &opt, int batch, int chunk,
+    unsigned int *counters, unsigned int *sync, int cooperative, FlowDfLaunch *out);
+cudaError_t flow_df_tc_launch(const FlowDfLaunch &l, TcStatus *status, cudaStream_t s);
 
 cudaError_t launch_maxpool2(const __half *in, __half *out, int batch, int h, int w, int c, cudaStream_t s);
 cudaError_t launch_upscale2(const __half *in, __half *out, int batch, int h, int w, int c, cudaStream_t s);

@@ -77,8 +77,9 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 struct Waiter {
 	TcStatus *status;
 	int kernel_id;
+	int layer;  // context reported with a time-out (persistent kernels keep it up to date)
 	bool dead;
-	__device__ __forceinline__ Waiter(TcStatus *s, int id) : status(s), kernel_id(id), dead(false) {}
+	__device__ __forceinline__ Waiter(TcStatus *s, int id) : status(s), kernel_id(id), layer(0), dead(false) {}
 
 	// converged-warp roles: one lane's abort is everybody's
 	__device__ __forceinline__ void sync_warp() { dead = __any_sync(0xffffffffu, dead) != 0; }
@@ -87,9 +88,13 @@ struct Waiter {
 		dead = true;
 		if (!status) return;
 		const int v = (kernel_id << 8) | code;
+		atomicOr(&status->pending, 1u << (code & 31));
 		if (atomicCAS(&status->code, 0, v) == 0) {
+			const int where = (layer << 16) | static_cast<int>(blockIdx.x & 0xffffu);
+			status->where = where;
 			int *h = status->host_code;
 			if (h) {
+				*reinterpret_cast<volatile int *>(h + 1) = where;
 				*reinterpret_cast<volatile int *>(h) = v;
 				__threadfence_system();
 			}
@@ -112,6 +117,7 @@ struct Waiter {
 	// a global-memory poll loop (dataflow counters) calls this every few hundred spins
 	__device__ __forceinline__ bool poll_expired(unsigned long long t0, int code) {
 		if (status && *reinterpret_cast<volatile int *>(&status->code) != 0) {
+			atomicOr(&status->pending, 1u << (code & 31));
 			dead = true;
 			return true;
 		}
@@ -233,6 +239,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 	      "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
 	    : "r"(taddr)
 	    : "memory");
+}
+
+// GPU-scope loads of the dataflow counters: relaxed while spinning (no L1 invalidation per poll),
+// one acquire once the expected value has been seen
+__device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int *p) {
+	unsigned int v;
+	asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p) {
+	unsigned int v;
+	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
 }
 
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }

@@ -93,18 +93,6 @@ __device__ __forceinline__ void ld_global_256(const __half *p, uint4 &a, uint4 &
 	             : "memory");
 }
 
-__device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int *p) {
-	unsigned int v;
-	asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-	return v;
-}
-
-__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p) {
-	unsigned int v;
-	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-	return v;
-}
-
 __global__ void __launch_bounds__(kThreadsT, 1)
 trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
 	extern __shared__ uint8_t smem_raw[];

@@ -227,6 +227,11 @@ def test_dataflow_trunk_race_stress(tmp_path):
     {"JU_TAIL_BANDS": "1"},
     {"JU_TRUNK_LEAD": "0"},
     {"JU_TAIL_BANDS": "5", "JU_NO_GRAPH": "1"},
+    {"JU_FUSED_FLOW": "1"},
+    {"JU_FUSED_FLOW": "1", "JU_FLOW_SUBBATCH": "1"},
+    {"JU_FUSED_FLOW": "1", "JU_FLOW_SUBBATCH": "2", "JU_TC_DUAL": "0"},
+    {"JU_TRUNK_COOP": "0"},
+    {"JU_COPY_THREADS": "0"},
 ])
 def test_execution_switches_do_not_change_the_bytes(tmp_path, env):
     """Scheduling / fusion switches only change HOW the frame is executed:
@@ -252,9 +257,6 @@ def test_execution_switches_do_not_change_the_bytes(tmp_path, env):
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
-        # the conv_tc switches are process-global once set: back to their defaults
-        jrt.set_option("tc_dual", 1)
-        jrt.set_option("tc_pdl", 1)
     for t in range(3):
         np.testing.assert_array_equal(got_s[t], want_s[t])
         np.testing.assert_array_equal(want_s[t], want_b[t][0])
