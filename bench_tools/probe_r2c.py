@@ -1,0 +1,53 @@
+"""Round-2 probe (GPU): CTA-pair (cta_group::2) persistent trunk vs the single-CTA trunk."""
+
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from joshupscale_b200 import config as jcfg  # noqa: E402
+from joshupscale_b200 import runtime as jrt  # noqa: E402
+from joshupscale_b200 import synthetic  # noqa: E402
+from joshupscale_b200 import weights as jw  # noqa: E402
+
+
+def run(preset, batch, env):
+    for k, v in env.items():
+        os.environ[k] = v
+    try:
+        cfg = jcfg.preset(preset)
+        w = jw.init_weights(cfg, 42, True)
+        with tempfile.TemporaryDirectory() as d:
+            path = os.path.join(d, "m.jup")
+            jw.save_model(path, cfg, w)
+            frames = [synthetic.frames(cfg.frame_height, cfg.frame_width, 2, stream_id=s) for s in range(batch)]
+            with jrt.Runtime(path, 0, batch) as rt:
+                outs = [np.stack(rt.process_batch([f[t] for f in frames])) for t in range(2)]
+                ops = rt.profile_ops(20)
+        groups = {o["name"][6:]: round(o["usec"], 1) for o in ops if o["name"].startswith("group:")}
+        return np.stack(outs), groups, None
+    except Exception as e:  # noqa: BLE001
+        return None, None, repr(e)
+    finally:
+        for k in env:
+            os.environ.pop(k, None)
+
+
+def main():
+    for preset, batch in (("small", 1), ("psp_fast", 1), ("psp_quality", 1), ("psp_quality", 2), ("psp_quality", 16)):
+        base, g0, err = run(preset, batch, {})
+        print(json.dumps({"preset": preset, "batch": batch, "env": {}, "groups": g0, "error": err}), flush=True)
+        for env in ({"JU_TRUNK_PAIR": "1"}, {"JU_TRUNK_PAIR": "1", "JU_TRUNK_COOP": "0"}):
+            out, g, err = run(preset, batch, env)
+            same = None if out is None or base is None else bool(np.array_equal(out, base))
+            print(json.dumps({"preset": preset, "batch": batch, "env": env, "groups": g, "bit_identical": same,
+                              "error": err}), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -583,9 +583,14 @@ int ju_launch_tail(const void *trunk, const void *w1, const float *bias1, const 
 		a.in = static_cast<const __half *>(trunk);
 		a.cin_stride = 64;
 		a.weights1 = w1;
-		a.bias1 = bias1;
-		a.w2 = w2;
-		a.bias2 = bias2;
+		// the kernel takes these small tensors as parameters: fetch them from the device
+		std::vector<float> hb1(128), hw2(4 * 3 * 32), hb2(3);
+		JU_CUDA(cudaMemcpy(hb1.data(), bias1, hb1.size() * sizeof(float), cudaMemcpyDeviceToHost));
+		JU_CUDA(cudaMemcpy(hw2.data(), w2, hw2.size() * sizeof(float), cudaMemcpyDeviceToHost));
+		JU_CUDA(cudaMemcpy(hb2.data(), bias2, hb2.size() * sizeof(float), cudaMemcpyDeviceToHost));
+		a.bias1_host = hb1.data();
+		a.w2_host = hw2.data();
+		a.bias2_host = hb2.data();
 		a.io = io.get();
 		a.pre_gen_next = static_cast<__half *>(pre_gen_next);
 		a.out_raw = out_raw;

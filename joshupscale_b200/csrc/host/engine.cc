@@ -196,6 +196,7 @@ ConvLayer *Engine::addConv(const std::string &name, const FoldedConv &f, int act
 	}
 	layer->bias = DeviceBuffer(f.bias.size() * sizeof(float));
 	layer->bias.upload(f.bias.data(), f.bias.size() * sizeof(float));
+	layer->biasHost = f.bias;
 	ConvLayer *raw = layer.get();
 	m_LayerByName[name] = raw;
 	m_Layers.push_back(std::move(layer));
@@ -247,8 +248,11 @@ void Engine::buildLayers(const ModelFile &model) {
 	m_W2 = DeviceBuffer(w2.size() * sizeof(float));
 	m_W2.upload(w2.data(), w2.size() * sizeof(float));
 	const auto &b2 = model.tensor("generator/conv_trans_2/bias").data;
+	if (b2.size() != 3) throw ModelException("conv_trans_2 bias must have 3 entries");
 	m_B2 = DeviceBuffer(3 * sizeof(float));
 	m_B2.upload(b2.data(), 3 * sizeof(float));
+	m_W2Host = w2;  // the fused tail kernel takes both as kernel parameters
+	m_B2Host = b2;
 }
 
 // ---------------------------------------------------------------------------
@@ -841,6 +845,7 @@ __half *Engine::emitTrunk(std::vector<Op> &plan, TrunkState &ts, const std::stri
 	const double leadFlops = lead ? 2.0 * H * W * 9.0 * lead->cinReal * 64 : 0.0;
 	TcStatus *status = m_Status.as<TcStatus>();
 	ta.cooperative = m_TrunkCooperative ? 1 : 0;
+	ta.pair = envInt("JU_TRUNK_PAIR", 0) != 0 ? 1 : 0;
 	for (int b0 = 0; b0 < B; b0 += chunk) {
 		TrunkArgs sub = ta;
 		sub.batch = std::min(chunk, B - b0);
@@ -878,9 +883,9 @@ void Engine::emitTail(std::vector<Op> &plan, int parity, const __half *trunkOut,
 	ta.in = trunkOut + static_cast<std::size_t>(H) * W * gs * b0;
 	ta.cin_stride = gs;
 	ta.weights1 = ct1->wTc.get();
-	ta.bias1 = ct1->bias.as<float>();
-	ta.w2 = m_W2.as<float>();
-	ta.bias2 = m_B2.as<float>();
+	ta.bias1_host = ct1->biasHost.data();
+	ta.w2_host = m_W2Host.data();
+	ta.bias2_host = m_B2Host.data();
 	ta.io = io;
 	ta.pre_gen_next = m_FilterOn ? m_OutRaw.as<__half>() + hrStream * b0 : preGenNext;
 	ta.out_raw = nullptr;

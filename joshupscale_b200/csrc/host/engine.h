@@ -37,6 +37,7 @@ struct ConvLayer {
 	DeviceBuffer wSimt;
 	DeviceBuffer wTc;
 	DeviceBuffer bias;
+	std::vector<float> biasHost;
 };
 
 struct Op {
@@ -163,6 +164,7 @@ private:
 
 	DeviceBuffer m_FlowIn[2], m_PreGen[2];
 	DeviceBuffer m_FlowHead, m_GenIn, m_Trunk[3], m_Mid, m_W2, m_B2;
+	std::vector<float> m_W2Host, m_B2Host;
 	bool m_FilterOn = false;
 	FilterParams m_Filter{};
 	DeviceBuffer m_OutRaw, m_FilterScratch;

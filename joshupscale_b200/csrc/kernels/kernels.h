@@ -114,10 +114,12 @@ void conv_tc_pack_weights(const float *kernel, const float *scale, int ksize, in
 struct TailArgs {
 	const __half *in;       // trunk output [batch, h, w, cin_stride] (64 live channels)
 	int cin_stride;
-	const void *weights1;   // conv_trans_1 as 1x1 conv to 128 ch, packed by conv_tc_pack_weights
-	const float *bias1;     // [128]
-	const float *w2;        // [4][3][32]
-	const float *bias2;     // [3]
+	const void *weights1;   // conv_trans_1 as 1x1 conv to 128 ch, packed by conv_tc_pack_weights (device)
+	// HOST copies (they become kernel parameters): conv_trans_1's folded BN bias [>= 32], conv_trans_2
+	// [4][3][32] and its bias [3]
+	const float *bias1_host;
+	const float *w2_host;
+	const float *bias2_host;
 	const FrameIO *io;
 	__half *pre_gen_next;   // [batch, 4h, 4w, 4]
 	float *out_raw;         // optional
@@ -131,7 +133,7 @@ struct TailArgs {
 struct TailTcLaunch {
 	alignas(64) unsigned char map_a[128];
 	alignas(64) unsigned char map_b[128];
-	alignas(8) unsigned char params[160];
+	alignas(8) unsigned char params[1856];
 	int grid;
 	unsigned int smem_bytes;
 	int pdl;
@@ -159,6 +161,9 @@ struct TrunkArgs {
 	// grid are resident together, which the inter-CTA dependencies of this kernel need when other
 	// work (another process under MPS, another stream) may occupy SMs
 	int cooperative;
+	// CTA pairs (clusters of two): one tcgen05.mma.cta_group::2 per two pixel tiles, each CTA holds
+	// half of the weights
+	int pair;
 };
 struct TrunkTcLaunch {
 	alignas(64) unsigned char maps[8 * 128];
@@ -167,6 +172,7 @@ struct TrunkTcLaunch {
 	unsigned int smem_bytes;
 	unsigned int *sync_counter;
 	int cooperative;
+	int pair;
 };
 // (trunk_df_tc.cu) per-wave completion counters between layers, no grid-wide barrier
 cudaError_t trunk_df_tc_prepare(const TrunkArgs &a, TrunkTcLaunch *out);

@@ -42,9 +42,12 @@ struct TailParams {
 	int act;
 	float slope;
 	int pdl;
-	const float *bias1;  // [128] folded BN bias of conv_trans_1, channel q*32+o
-	const float *w2;     // [4][3][32] conv_trans_2 (s = i2*2+j2, o, c), fp16-representable values
-	const float *bias2;  // [3]
+	// conv_trans_2 (s = i2*2+j2, o, c; fp16-representable values), its bias and the folded BN bias of
+	// conv_trans_1 (the same 32 values for each of its 4 sub-pixels) travel IN the kernel parameters:
+	// the unrolled epilogue reads them as constant-bank operands instead of 96 LDS.128 per thread
+	float w2[4 * 3 * 32];
+	float bias2[4];
+	float bias1[32];
 	const FrameIO *io;
 	__half *pre_gen_next;  // [batch,4H,4W,4]
 	float *out_raw;        // optional [batch,4H,4W,3]
@@ -81,8 +84,7 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 	const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
 	uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 	const uint32_t b_base = smem_base + kStages * kATile;
-	const uint32_t w2_off = kStages * kATile + kBBytes;          // 384 floats
-	const uint32_t bar_base = smem_base + w2_off + 2048u;
+	const uint32_t bar_base = smem_base + kStages * kATile + kBBytes;
 	auto full_bar = [&](int s) { return bar_base + 8u * s; };
 	auto empty_bar = [&](int s) { return bar_base + 8u * (8 + s); };
 	auto tfull_bar = [&](int s) { return bar_base + 8u * (16 + s); };
@@ -111,13 +113,6 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 		             "r"(kTmemCols)
 		             : "memory");
 		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-	}
-	// conv_trans_2 weights + biases -> shared (constants, independent of the previous kernel)
-	{
-		float *w2s = reinterpret_cast<float *>(smem_gen + w2_off);
-		for (int t = threadIdx.x; t < 384; t += kThreads) w2s[t] = p.w2[t];
-		if (threadIdx.x < 3) w2s[384 + threadIdx.x] = p.bias2[threadIdx.x];
-		if (threadIdx.x < 32) w2s[388 + threadIdx.x] = p.bias1[threadIdx.x];
 	}
 	tcgen05_fence_before();
 	__syncthreads();
@@ -192,8 +187,7 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 		const int q = (warp - 2) >> 2;     // sub-pixel handled by this warp
 		const int i = q >> 1, j = q & 1;
 		const int row = q4 * 32 + lane;
-		const float *w2s = reinterpret_cast<const float *>(smem_gen + w2_off);
-		const float b2[3] = {w2s[384], w2s[385], w2s[386]};
+		const float b2[3] = {p.bias2[0], p.bias2[1], p.bias2[2]};
 		Waiter W(p.status, TC_KERNEL_TAIL);
 		if (p.pdl) grid_dependency_wait();
 		const int H4 = 4 * p.h, W4 = 4 * p.w;
@@ -236,8 +230,7 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 			float m[32];
 #pragma unroll
 			for (int c4 = 0; c4 < 8; ++c4) {
-				const float4 bv = *reinterpret_cast<const float4 *>(w2s + 388 + c4 * 4);
-				const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+				const float bb[4] = {p.bias1[c4 * 4], p.bias1[c4 * 4 + 1], p.bias1[c4 * 4 + 2], p.bias1[c4 * 4 + 3]};
 #pragma unroll
 				for (int e = 0; e < 4; ++e) {
 					float v = __uint_as_float(acc[c4 * 4 + e]) + bb[e];
@@ -266,9 +259,9 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 				for (int s2 = 0; s2 < 4; ++s2) {
 #pragma unroll
 					for (int o = 0; o < 3; ++o) {
-						const ulonglong2 wv = *reinterpret_cast<const ulonglong2 *>(w2s + (s2 * 3 + o) * 32 + c4 * 4);
-						ffma2(zp[s2][o], mp[c4 * 2 + 0], wv.x);
-						ffma2(zp[s2][o], mp[c4 * 2 + 1], wv.y);
+						const float *wq = p.w2 + (s2 * 3 + o) * 32 + c4 * 4;
+						ffma2(zp[s2][o], mp[c4 * 2 + 0], pack2(wq[0], wq[1]));
+						ffma2(zp[s2][o], mp[c4 * 2 + 1], pack2(wq[2], wq[3]));
 					}
 				}
 			}
@@ -343,7 +336,7 @@ EncodeTiledFn encodeTiled() {
 	return fn;
 }
 
-constexpr uint32_t kSmemBytes = 1024u + kStages * kATile + kBBytes + 2048u + 256u;
+constexpr uint32_t kSmemBytes = 1024u + kStages * kATile + kBBytes + 256u;
 
 }  // namespace
 
@@ -369,9 +362,10 @@ cudaError_t tail_tc_prepare(const TailArgs &a, TailTcLaunch *out) {
 	p.act = a.act;
 	p.slope = a.slope;
 	p.pdl = a.pdl;
-	p.bias1 = a.bias1;
-	p.w2 = a.w2;
-	p.bias2 = a.bias2;
+	if (!a.w2_host || !a.bias2_host || !a.bias1_host) return cudaErrorInvalidValue;
+	std::memcpy(p.w2, a.w2_host, sizeof(p.w2));
+	std::memcpy(p.bias2, a.bias2_host, 3 * sizeof(float));
+	std::memcpy(p.bias1, a.bias1_host, sizeof(p.bias1));
 	p.io = a.io;
 	p.pre_gen_next = a.pre_gen_next;
 	p.out_raw = a.out_raw;

@@ -59,6 +59,12 @@ constexpr uint32_t kABox = 18u * 10u * 128u;
 constexpr uint32_t kARegion = (kABox + 1023u) & ~1023u;
 constexpr uint32_t kBSlice = 64u * 128u;
 constexpr uint32_t kBBytes = 9u * kBSlice;  // one layer's weights
+// CTA-pair version (PAIR): a cluster of two CTAs issues one tcgen05.mma.cta_group::2 (M = 256) for
+// both pixel tiles; each CTA supplies its own halo and HALF of the weights (32 of the 64 output
+// channels' rows).  Measured issue rate of the bare MMA stream: 43 instead of 48 cycles
+// (profiles/r02_mma_rate2.txt) - the weight fetch is what the pair shares.
+constexpr uint32_t kBSliceP = 32u * 128u;
+constexpr uint32_t kBBytesP = 9u * kBSliceP;
 constexpr uint32_t kEpiTile = 128u * 128u;
 constexpr int kAccStages = 4;  // TMEM accumulator stages of 64 columns
 
@@ -85,6 +91,55 @@ struct TrunkMaps {
 	CUtensorMap w;        // weights of all layers: rows [layer][tap][cout], 64 ch each
 };
 
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+	uint32_t r;
+	asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+	return r;
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+	uint32_t r;
+	asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+	return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+	asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+	asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+	asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads of a CTA pair: the data lands in the issuing CTA, the bytes are counted on the barrier
+// at `bar_cluster` (the leader's)
+__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar_cluster, int c0, int c1, int c2,
+    int c3) {
+	asm volatile(
+	    "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+	    " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+	    "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+	    : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar_cluster, int c0, int c1) {
+	asm volatile(
+	    "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+	    " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+	    "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
+	    : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+	asm volatile(
+	    "{\n\t.reg .pred p;\n\t"
+	    "setp.ne.b32 p, %4, 0;\n\t"
+	    "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+	    "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+	    : "memory");
+}
+// arrive on the barrier at this CTA-relative offset in both CTAs of the pair
+__device__ __forceinline__ void umma2_commit_both(uint32_t bar) {
+	asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+	    "h"(static_cast<uint16_t>(3))
+	    : "memory");
+}
+
 // 32 bytes (16 channels) from L2, bypassing L1
 __device__ __forceinline__ void ld_global_256(const __half *p, uint4 &a, uint4 &b) {
 	asm volatile("ld.global.cg.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -93,13 +148,20 @@ __device__ __forceinline__ void ld_global_256(const __half *p, uint4 &a, uint4 &
 	             : "memory");
 }
 
+template <bool PAIR>
 __global__ void __launch_bounds__(kThreadsT, 1)
 trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) {
 	extern __shared__ uint8_t smem_raw[];
 	const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
 	uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 	const uint32_t resb_base = smem_base + static_cast<uint32_t>(p.stages) * kARegion;
-	const uint32_t epi_out_base = resb_base + kBBytes;
+	constexpr uint32_t kSlice = PAIR ? kBSliceP : kBSlice;  // this CTA's rows of one tap's weights
+	const uint32_t epi_out_base = resb_base + 9u * kSlice;
+	// PAIR: the two CTAs of a cluster work on tiles 2i, 2i+1 of every round; rank 0 issues the MMAs
+	const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+	const bool leader = rank == 0;
+	// first tile of this CTA's (pair's) first round: tile = first + round * grid (+ rank)
+	const int first = PAIR ? static_cast<int>(blockIdx.x & ~1u) : static_cast<int>(blockIdx.x);
 	const uint32_t bar_base = epi_out_base + kStoreWarps * kEpiTile;
 	auto full_bar = [&](int s) { return bar_base + 8u * s; };
 	auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
@@ -122,7 +184,7 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 		}
 		for (int s = 0; s < kAccStages; ++s) {
 			mbar_init(tfull_bar(s), 1);
-			mbar_init(tempty_bar(s), 8);
+			mbar_init(tempty_bar(s), PAIR ? 16 : 8);  // the leader's barrier also counts the partner's epilogue warps
 		}
 		for (int s = 0; s < kStoreWarps; ++s) {
 			mbar_init(sready_bar(s), 8);
@@ -135,13 +197,22 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	if (warp == 1) {
-		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
-		             "r"(kTmemCols)
-		             : "memory");
-		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+		if (PAIR) {
+			asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols)
+			             : "memory");
+			asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+		} else {
+			asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols)
+			             : "memory");
+			asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+		}
 	}
 	tcgen05_fence_before();
-	__syncthreads();
+	if (PAIR) {
+		cluster_sync_all();  // the partner's barriers are initialised, its TMEM allocated
+	} else {
+		__syncthreads();
+	}
 	tcgen05_fence_after();
 	uint32_t tmem_base;
 	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
@@ -182,6 +253,10 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 	// (blockIdx.x + tiles_x + 1) % grid in wave k + (blockIdx.x + tiles_x + 1) / grid - so the first
 	// grid - tiles_x - 1 CTAs only need wave k itself, which was stored a full tile period earlier
 	const int wave_reach = (static_cast<int>(blockIdx.x) + p.tiles_x + 1) / static_cast<int>(gridDim.x);
+	// PAIR: the last round may hold a tile without a partner; the partner then runs a dummy tile
+	// (coordinates beyond the batch: TMA loads zero-fill it, the TMA store clips it) that neither
+	// waits for nor publishes anything
+	auto my_tile = [&](int base) { return PAIR ? base + static_cast<int>(rank) : base; };
 
 	if (warp == 0 || warp == kSecondProducerWarp) {
 		const int pme = warp == 0 ? 0 : 1;  // two producers, alternating tiles
@@ -192,7 +267,8 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 		for (int l = 0; l < p.n_layers; ++l) {
 			const CUtensorMap *min = &maps.in[layer_in(l)];
 			int known = -1;  // highest wave of layer l-1 known to be completely stored
-			for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+			for (int base = first; base < p.total_tiles; base += gridDim.x, ++it) {
+				const int tile = my_tile(base);
 				int b, y0, x0;
 				decode(tile, b, y0, x0);
 				if ((it & 1) != pme) continue;
@@ -201,7 +277,7 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 				W.wait(empty_bar(s), ph ^ 1u, 1);
 				W.sync_warp();
 				bool polled = false;
-				if (l > 0 && !W.dead) {
+				if (l > 0 && !W.dead && tile < p.total_tiles) {
 					// waves <= k+1 of layer l-1 must be completely stored (covers the 3x3 neighbourhood)
 					const int k = (tile - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x);
 					const int needw = k + wave_reach < n_waves ? k + wave_reach : n_waves - 1;
@@ -241,8 +317,14 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 						// order the async-proxy (TMA) reads below after the acquire loads above
 						asm volatile("fence.proxy.async;" ::: "memory");
 					}
-					mbar_arrive_expect_tx(full_bar(s), kABox);
-					tma_load_4d(smem_base + s * kARegion, min, full_bar(s), 0, x0 - 1, y0 - 1, b);
+					if (PAIR) {
+						// both halos of the pair are counted on the leader's barrier
+						if (leader) mbar_arrive_expect_tx(full_bar(s), 2u * kABox);
+						tma2_load_4d(smem_base + s * kARegion, min, mapa(full_bar(s), 0), 0, x0 - 1, y0 - 1, b);
+					} else {
+						mbar_arrive_expect_tx(full_bar(s), kABox);
+						tma_load_4d(smem_base + s * kARegion, min, full_bar(s), 0, x0 - 1, y0 - 1, b);
+					}
 				}
 				__syncwarp();
 			}
@@ -255,8 +337,15 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 				for (int t = 0; t < 9; ++t) {
 					if (l > 0) W.wait(wempty_tap(t), static_cast<uint32_t>((l - 1) & 1), 9);
 					if (W.dead) continue;
-					mbar_arrive_expect_tx(wfull_tap(t), kBSlice);
-					tma_load_2d(resb_base + t * kBSlice, &maps.w, wfull_tap(t), 0, (l * 9 + t) * 64);
+					if (PAIR) {
+						// this CTA's 32 rows of the tap; both halves are counted on the leader's barrier
+						if (leader) mbar_arrive_expect_tx(wfull_tap(t), 2u * kBSliceP);
+						tma2_load_2d(resb_base + t * kBSliceP, &maps.w, mapa(wfull_tap(t), 0), 0,
+						    (l * 9 + t) * 64 + static_cast<int>(rank) * 32);
+					} else {
+						mbar_arrive_expect_tx(wfull_tap(t), kBSlice);
+						tma_load_2d(resb_base + t * kBSlice, &maps.w, wfull_tap(t), 0, (l * 9 + t) * 64);
+					}
 				}
 			}
 		}
@@ -275,7 +364,8 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 			int it = 0;
 			for (int l = 0; l < p.n_layers; ++l) {
 				const CUtensorMap *mout = &maps.tile[layer_out(l)];
-				for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+				for (int base = first; base < p.total_tiles; base += gridDim.x, ++it) {
+					const int tile = my_tile(base);
 					if (it % kStoreWarps != me) continue;
 					int b, y0, x0;
 					decode(tile, b, y0, x0);
@@ -290,10 +380,8 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 					// the bulk store has completed (async proxy): order it before the generic-proxy
 					// release below, which makes it visible to every acquiring producer warp
 					asm volatile("fence.proxy.async;" ::: "memory");
-					if (stall) continue;
-					asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(
-					                 p.flags + l * n_waves +
-					                 (tile - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x))
+					if (stall || tile >= p.total_tiles) continue;
+					asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.flags + l * n_waves + (base - first) / static_cast<int>(gridDim.x))
 					             : "memory");
 				}
 			}
@@ -305,6 +393,8 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 				atomicAdd(p.sync_counter + 1, 1u);
 			}
 		}
+	} else if ((warp == 1 || warp == kSecondMmaWarp) && !leader) {
+		// PAIR: the partner's issuer warps have nothing to do - the leader issues for both CTAs
 	} else if (warp == 1 || warp == kSecondMmaWarp) {
 		// ===================== MMA issuers (two warps, alternating tiles) =====================
 		// A barrier check has to get through the shared-memory pipe that the UMMA operand fetch
@@ -314,13 +404,23 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 		// only the resident weights couple them, see `pos` below.
 		const int mi = warp == 1 ? 0 : 1;
 		Waiter W(p.status, TC_KERNEL_TRUNK);
-		const uint32_t idesc = make_idesc(64);
+		// PAIR: the commit arrives on the same barrier of BOTH CTAs (stage free, accumulator ready,
+		// weight tap free)
+		auto commit = [&](uint32_t bar) {
+			if (PAIR) {
+				umma2_commit_both(bar);
+			} else {
+				umma_commit(bar);
+			}
+		};
+		// PAIR: M = 256 (128 rows per CTA), N = 64
+		const uint32_t idesc = PAIR ? ((1u << 4) | (static_cast<uint32_t>(64 >> 3) << 17) | (static_cast<uint32_t>(256 >> 4) << 24))
+		                            : make_idesc(64);
 		const uint32_t a_hi = static_cast<uint32_t>(make_smem_desc(0, 1280u, 0) >> 32);
 		const uint32_t b_hi = static_cast<uint32_t>(make_smem_desc(0, 1024u, 0) >> 32);
 		const uint32_t lo_flags = 1u << 16;
 		// tiles of this CTA per layer
-		const int cnt = (p.total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
-		                static_cast<int>(gridDim.x);
+		const int cnt = first < p.total_tiles ? (p.total_tiles - first + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x) : 0;
 		int it = 0;
 		for (int l = 0; l < p.n_layers; ++l) {
 			for (int pos = 0; pos < cnt; ++pos, ++it) {
@@ -346,20 +446,24 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 						if (fresh) W.wait(wfull_tap(tap), static_cast<uint32_t>(l & 1), 2);
 						if (W.dead) break;  // aborted frame: nothing is issued or committed any more
 						const uint32_t a_tap = a_lo + (tap / 3) * 80u + (tap % 3) * 8u;
-						const uint32_t b_tap = b_lo + tap * (kBSlice >> 4);
+						const uint32_t b_tap = b_lo + tap * (kSlice >> 4);
 #pragma unroll
 						for (int k16 = 0; k16 < 4; ++k16) {
 							const uint64_t a_desc = (static_cast<uint64_t>(a_hi) << 32) | (a_tap + k16 * 2u);
 							const uint64_t b_desc = (static_cast<uint64_t>(b_hi) << 32) | (b_tap + k16 * 2u);
-							umma_f16(d_tmem, a_desc, b_desc, idesc, (tap | k16) != 0 ? 1u : 0u);
+							if (PAIR) {
+								umma2_f16(d_tmem, a_desc, b_desc, idesc, (tap | k16) != 0 ? 1u : 0u);
+							} else {
+								umma_f16(d_tmem, a_desc, b_desc, idesc, (tap | k16) != 0 ? 1u : 0u);
+							}
 						}
 						// this tap's slice may be overwritten once these MMAs (of both issuers) retire
-						if (releases >= 1) umma_commit(wempty_tap(tap));
-						if (releases == 2) umma_commit(wempty_tap(tap));
+						if (releases >= 1) commit(wempty_tap(tap));
+						if (releases == 2) commit(wempty_tap(tap));
 					}
 					if (!W.dead) {
-						umma_commit(empty_bar(s));
-						umma_commit(tfull_bar(as));
+						commit(empty_bar(s));
+						commit(tfull_bar(as));
 					}
 				}
 				__syncwarp();
@@ -383,7 +487,8 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 			for (int c = 0; c < 32; ++c) bias_reg[c] = __ldg(p.bias + l * 64 + half * 32 + c);
 			const bool has_res = layer_res(l) >= 0;
 			const __half *res_buf = has_res ? p.buffers[layer_res(l)] : nullptr;
-			for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+			for (int base = first; base < p.total_tiles; base += gridDim.x, ++it) {
+				const int tile = my_tile(base);
 				const int as = it % kAccStages;
 				const uint32_t aph = (it / kAccStages) & 1;
 				const int ss = it % kStoreWarps;  // staging tile
@@ -397,7 +502,7 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 					int b, y0, x0;
 					decode(tile, b, y0, x0);
 					const int y = y0 + (row >> 3), x = x0 + (row & 7);
-					if (y < p.h && x < p.w) {
+					if (tile < p.total_tiles && y < p.h && x < p.w) {
 						const __half *src = res_buf +
 						    ((static_cast<size_t>(b) * p.h + y) * p.w + x) * static_cast<size_t>(p.cstride) + half * 32;
 						ld_global_256(src, res[0], res[1]);
@@ -417,7 +522,13 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 				tcgen05_fence_before();
 				__syncwarp();
 				W.sync_warp();
-				if (lane == 0 && !W.dead) mbar_arrive(tempty_bar(as));
+				if (lane == 0 && !W.dead) {
+					if (PAIR) {
+						mbar_arrive_cluster(mapa(tempty_bar(as), 0));  // the leader's MMA warps own the accumulators of both CTAs
+					} else {
+						mbar_arrive(tempty_bar(as));
+					}
+				}
 				W.wait(sfree_bar(ss), sph ^ 1u, 11);  // staging[ss] consumed by the store of tile it-2
 				float v[32];
 #pragma unroll
@@ -462,12 +573,21 @@ trunk_df_tc_kernel(const __grid_constant__ TrunkMaps maps, const TrunkParams p) 
 		}
 	}
 
+	// PAIR: the leader's MMAs read the partner's shared memory and the partner arrives on the
+	// leader's barriers: neither CTA may exit (or free TMEM) before both are done
 	tcgen05_fence_before();
-	__syncthreads();
+	if (PAIR) {
+		cluster_sync_all();
+	} else {
+		__syncthreads();
+	}
 	if (warp == 1) {
 		tcgen05_fence_after();
-		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols)
-		             : "memory");
+		if (PAIR) {
+			asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+		} else {
+			asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+		}
 	}
 }
 
@@ -490,6 +610,7 @@ EncodeTiledFn encodeTiledDF() {
 }
 
 constexpr uint32_t kFixed = 1024u + 768u + kBBytes + kStoreWarps * kEpiTile;  // alignment slack, barriers, weights, staging
+constexpr uint32_t kFixedP = 1024u + 768u + kBBytesP + kStoreWarps * kEpiTile;  // CTA pair: half of the weights per CTA
 
 }  // namespace
 
@@ -518,7 +639,8 @@ cudaError_t trunk_df_tc_prepare(const TrunkArgs &a, TrunkTcLaunch *out) {
 	for (int i = 0; i < 3; ++i) p.buffers[i] = static_cast<const __half *>(a.buffers[i]);
 	p.cstride = a.cstride;
 	p.lead = lead;
-	int stages = static_cast<int>((kSmemLimit - kFixed) / kARegion);
+	const bool pair = a.pair != 0;
+	int stages = static_cast<int>((kSmemLimit - (pair ? kFixedP : kFixed)) / kARegion);
 	if (stages > kMaxStages) stages = kMaxStages;
 	// The two producer / issuer pairs take tiles alternately.  With an EVEN stage count each pair
 	// owns a disjoint set of halo stages, i.e. two independent single-producer / single-consumer
@@ -558,7 +680,7 @@ cudaError_t trunk_df_tc_prepare(const TrunkArgs &a, TrunkTcLaunch *out) {
 	{
 		cuuint64_t wd[2] = {64, static_cast<cuuint64_t>(a.n_layers) * 9 * 64};
 		cuuint64_t ws[1] = {128};
-		cuuint32_t wb[2] = {64, 64};
+		cuuint32_t wb[2] = {64, pair ? 32u : 64u};  // CTA pair: each CTA loads its 32 rows of a tap
 		if (encode(&maps.w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(a.weights), wd, ws, wb, estr,
 		        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
 		        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
@@ -568,15 +690,20 @@ cudaError_t trunk_df_tc_prepare(const TrunkArgs &a, TrunkTcLaunch *out) {
 	std::memcpy(out->maps, &maps, sizeof(maps));
 	std::memcpy(out->params, &p, sizeof(p));
 	// per device and cheap: set at every prepare (plan time), never on the launch path
-	cudaError_t attrErr = cudaFuncSetAttribute(trunk_df_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	    static_cast<int>(kSmemLimit));
+	cudaError_t attrErr = cudaFuncSetAttribute(pair ? trunk_df_tc_kernel<true> : trunk_df_tc_kernel<false>,
+	    cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemLimit));
 	if (attrErr != cudaSuccess) return attrErr;
 	int dev = 0, sms = 148;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-	// every CTA must be co-resident (grid barrier): at most one per SM
+	// every CTA must be co-resident (inter-CTA dependencies): at most one per SM; CTA pairs need an even grid
 	out->grid = p.total_tiles < sms ? p.total_tiles : sms;
-	out->smem_bytes = kFixed + static_cast<uint32_t>(p.stages) * kARegion;
+	if (pair) {
+		out->grid = (out->grid + 1) & ~1;
+		if (out->grid > sms) out->grid = sms & ~1;
+	}
+	out->pair = pair ? 1 : 0;
+	out->smem_bytes = (pair ? kFixedP : kFixed) + static_cast<uint32_t>(p.stages) * kARegion;
 	out->sync_counter = a.sync_counter;
 	out->cooperative = a.cooperative;
 	return cudaSuccess;
@@ -593,8 +720,15 @@ cudaError_t trunk_df_tc_launch(const TrunkTcLaunch &l, TcStatus *status, cudaStr
 	cfg.blockDim = dim3(kThreadsT);
 	cfg.dynamicSmemBytes = l.smem_bytes;
 	cfg.stream = s;
-	cudaLaunchAttribute attr[2];
+	cudaLaunchAttribute attr[3];
 	int n = 0;
+	if (l.pair) {
+		attr[n].id = cudaLaunchAttributeClusterDimension;
+		attr[n].val.clusterDim.x = 2;
+		attr[n].val.clusterDim.y = 1;
+		attr[n].val.clusterDim.z = 1;
+		++n;
+	}
 	if (p.pdl) {
 		attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
 		attr[n].val.programmaticStreamSerializationAllowed = 1;
@@ -607,7 +741,7 @@ cudaError_t trunk_df_tc_launch(const TrunkTcLaunch &l, TcStatus *status, cudaStr
 	}
 	cfg.attrs = attr;
 	cfg.numAttrs = n;
-	return cudaLaunchKernelEx(&cfg, trunk_df_tc_kernel, maps, p);
+	return l.pair ? cudaLaunchKernelEx(&cfg, trunk_df_tc_kernel<true>, maps, p) : cudaLaunchKernelEx(&cfg, trunk_df_tc_kernel<false>, maps, p);
 }
 
 }  // namespace ju

@@ -232,6 +232,8 @@ def test_dataflow_trunk_race_stress(tmp_path):
     {"JU_FUSED_FLOW": "1", "JU_FLOW_SUBBATCH": "2", "JU_TC_DUAL": "0"},
     {"JU_TRUNK_COOP": "0"},
     {"JU_COPY_THREADS": "0"},
+    {"JU_TRUNK_PAIR": "1"},
+    {"JU_TRUNK_PAIR": "1", "JU_TRUNK_COOP": "0", "JU_TRUNK_SUBBATCH": "1"},
 ])
 def test_execution_switches_do_not_change_the_bytes(tmp_path, env):
     """Scheduling / fusion switches only change HOW the frame is executed:
