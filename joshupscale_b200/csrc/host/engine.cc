@@ -139,6 +139,7 @@ Engine::~Engine() {
 	} restore{prev};
 	cudaStreamSynchronize(m_Stream);
 	cudaStreamSynchronize(m_CopyStream);
+	for (cudaEvent_t ev : m_BandEvents) cudaEventDestroy(ev);
 	destroyGraphsAndEvents();
 	cudaStreamDestroy(m_CopyStream);
 	cudaStreamDestroy(m_Stream);
@@ -1124,7 +1125,7 @@ void Engine::bindImages(int n, const ju_image *inputs, const ju_image *outputs) 
 		}
 	}
 	if (!pooledInputs.empty()) {
-		m_Pool->wait();
+		m_Pool->end();
 		for (int s : pooledInputs) {
 			JU_CUDA(cudaMemcpyAsync(m_InStage.as<std::uint8_t>() + s * H * inRow, m_InPinned.as<std::uint8_t>() + s * H * inRow,
 			    H * inRow, cudaMemcpyHostToDevice, m_Stream));
@@ -1190,11 +1191,6 @@ void Engine::ensureHostStaging() {
 	m_Pool = std::make_unique<HostCopyPool>(m_CopyThreads);
 }
 
-void CUDART_CB Engine::bandArrived(void *user) {
-	auto *band = static_cast<BandCopy *>(user);
-	band->pool->submit(band->job);
-}
-
 void Engine::unmapResources() {
 	if (m_MappedResources.empty()) return;
 	std::vector<cudaGraphicsResource_t> res;
@@ -1204,6 +1200,7 @@ void Engine::unmapResources() {
 
 void Engine::process(int n, const ju_image *inputs, const ju_image *outputs) {
 	if (n < 1 || n > m_Batch) throw std::invalid_argument("image count must be in [1, batch]");
+	m_BandEventsUsed = 0;
 	DeviceGuard guard(m_Device);
 	std::lock_guard<std::mutex> turn(deviceMutex(m_Device));  // see deviceMutex: one frame at a time per device
 	const std::size_t H = m_Spec.frameH, W = m_Spec.frameW, outRow = 4 * W * 4;
@@ -1220,7 +1217,7 @@ void Engine::process(int n, const ju_image *inputs, const ju_image *outputs) {
 		// Device-to-host copies of staged images run on a second stream, one group of streams at a
 		// time as soon as the frame graph has recorded that group's completion event: with several
 		// sub-batches the copies of the first streams overlap the trunk of the later ones.
-		bool copied = false, pooled = false;
+		bool copied = false;
 		m_BandCopies.clear();
 		for (const Region &r : m_Regions[variant]) {
 			const int b0 = r.b0, b1 = std::min(n, r.b0 + r.nb);
@@ -1237,18 +1234,17 @@ void Engine::process(int n, const ju_image *inputs, const ju_image *outputs) {
 				if (m_OutputPooled[s]) {
 					std::uint8_t *pinned = m_OutPinned.as<std::uint8_t>() + s * 4 * H * outRow + r.row0 * outRow;
 					JU_CUDA(cudaMemcpyAsync(pinned, stage + r.row0 * outRow, rows * outRow, cudaMemcpyDeviceToHost, m_CopyStream));
-					auto band = std::make_unique<BandCopy>();
-					band->pool = m_Pool.get();
-					band->job.dst = p + static_cast<std::ptrdiff_t>(r.row0) * static_cast<std::ptrdiff_t>(out.stride);
-					band->job.src = pinned;
-					band->job.dstStride = static_cast<std::ptrdiff_t>(out.stride);
-					band->job.srcStride = static_cast<std::ptrdiff_t>(outRow);
-					band->job.rowBytes = outRow;
-					band->job.rows = rows;
-					// runs on the copy stream right after the band has arrived in pinned memory
-					JU_CUDA(cudaLaunchHostFunc(m_CopyStream, &Engine::bandArrived, band.get()));
-					m_BandCopies.push_back(std::move(band));
-					pooled = true;
+					// the rows are scattered into the caller's image as soon as the band has arrived in
+					// pinned memory (event below); image row i lives at ptr + i * stride
+					BandCopy band;
+					band.job.dst = p + static_cast<std::ptrdiff_t>(r.row0) * static_cast<std::ptrdiff_t>(out.stride);
+					band.job.src = pinned;
+					band.job.dstStride = static_cast<std::ptrdiff_t>(out.stride);
+					band.job.srcStride = static_cast<std::ptrdiff_t>(outRow);
+					band.job.rowBytes = outRow;
+					band.job.rows = rows;
+					band.event = nullptr;
+					m_BandCopies.push_back(band);
 				} else if (out.stride == static_cast<std::int64_t>(outRow)) {
 					// dense image: one linear copy
 					JU_CUDA(cudaMemcpyAsync(p + r.row0 * outRow, stage + r.row0 * outRow, rows * outRow,
@@ -1266,6 +1262,17 @@ void Engine::process(int n, const ju_image *inputs, const ju_image *outputs) {
 				}
 				copied = true;
 			}
+			if (!m_BandCopies.empty() && !m_BandCopies.back().event) {
+				// one event per region: every pinned copy of the region queued above has landed
+				const std::size_t used = m_BandEventsUsed++;
+				if (used == m_BandEvents.size()) {
+					cudaEvent_t ev = nullptr;
+					JU_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+					m_BandEvents.push_back(ev);
+				}
+				JU_CUDA(cudaEventRecord(m_BandEvents[used], m_CopyStream));
+				for (auto it = m_BandCopies.rbegin(); it != m_BandCopies.rend() && !it->event; ++it) it->event = m_BandEvents[used];
+			}
 		}
 		// graphics-resource outputs: staging buffer -> mapped array, then unmap, all in stream order
 		for (int s = 0; s < n; ++s) {
@@ -1275,9 +1282,27 @@ void Engine::process(int n, const ju_image *inputs, const ju_image *outputs) {
 			    cudaMemcpyDeviceToDevice, m_Stream));
 		}
 		unmapResources();
+		if (!m_BandCopies.empty()) {
+			// pageable outputs: poll the bands in stream order, hand each to the copy pool as it
+			// arrives and copy along while waiting for the next one
+			m_Pool->begin();
+			cudaEvent_t ready = nullptr;
+			for (const BandCopy &band : m_BandCopies) {
+				if (band.event != ready) {
+					for (;;) {
+						const cudaError_t q = cudaEventQuery(band.event);
+						if (q == cudaSuccess) break;
+						if (q != cudaErrorNotReady) checkCuda(q, "cudaEventQuery");
+						m_Pool->help();
+					}
+					ready = band.event;
+				}
+				m_Pool->submit(band.job);
+			}
+			m_Pool->end();
+		}
 		JU_CUDA(cudaStreamSynchronize(m_Stream));
 		if (copied) JU_CUDA(cudaStreamSynchronize(m_CopyStream));
-		if (pooled) m_Pool->wait();  // every band's host function has run: all rows are queued or done
 		const int stall = *static_cast<volatile int *>(m_StatusHost.as<int>());
 		if (stall != 0) {
 			const int where = static_cast<volatile int *>(m_StatusHost.as<int>())[1];
@@ -1302,7 +1327,7 @@ void Engine::process(int n, const ju_image *inputs, const ju_image *outputs) {
 		}
 		cudaStreamSynchronize(m_Stream);
 		cudaStreamSynchronize(m_CopyStream);
-		if (m_Pool) m_Pool->wait();
+		if (m_Pool) m_Pool->end();
 		throw;
 	}
 	m_Parity ^= 1;

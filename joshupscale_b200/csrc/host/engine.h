@@ -119,7 +119,6 @@ private:
 	void unmapResources();
 	static bool isPageable(const void *ptr);
 	void ensureHostStaging();
-	static void CUDART_CB bandArrived(void *user);
 	void uploadStatus(int inject);
 	void recoverFromStall();
 
@@ -152,13 +151,15 @@ private:
 	std::vector<bool> m_OutputPooled;  // pageable output: device -> m_OutPinned -> copy pool -> caller
 	// pageable host images (the plugins' case): engine-owned pinned staging + a multi-threaded memcpy
 	struct BandCopy {
-		HostCopyPool *pool;
 		CopyJob job;
+		cudaEvent_t event;  // the band has arrived in pinned memory
 	};
 	int m_CopyThreads = 4;
 	std::unique_ptr<HostCopyPool> m_Pool;
 	PinnedBuffer m_InPinned, m_OutPinned;
-	std::vector<std::unique_ptr<BandCopy>> m_BandCopies;  // alive until the frame's streams are synchronised
+	std::vector<BandCopy> m_BandCopies;     // this frame's bands, in copy-stream order
+	std::vector<cudaEvent_t> m_BandEvents;  // reused from frame to frame
+	std::size_t m_BandEventsUsed = 0;
 	std::vector<cudaArray_t> m_OutputArrays;                 // per stream: mapped output array or null
 	std::vector<cudaGraphicsResource_t> m_MappedResources;  // mapped for the frame in flight
 
