@@ -557,13 +557,21 @@ void Engine::buildPlan(int parity, int variant) {
 		const bool tailPerChunk = m_ConvImpl == 1 && ct1c->wTc.get() && gs % 64 == 0 && s.genFilters == 64 &&
 		                          envInt("JU_FUSED_TAIL", 1) != 0;
 		bool tailsEmitted = false;
+		// the tail kernel wants >= 2 streams per launch (1020 tiles of one PSP stream are 6.9 waves on
+		// 148 SMs): finished trunk launches are collected until that many streams are waiting
+		const int tailGroup = std::max(1, envInt("JU_TAIL_GROUP", 2));
+		int tailB0 = 0, tailNb = 0;
 		cur = emitTrunk(plan, m_GenTrunk, "generator", s.genBlocks, t0, t1, t2, gs, H, W, conv1InTrunk ? gc1 : nullptr,
 		    m_GenIn.as<__half>(), [&](const __half *out, int b0, int nb, bool wholeBatch) {
 			    // With several sub-batches each one is finished right away (tail kernel, output filter)
 			    // and its completion is published as an event, so that process() can copy these streams'
 			    // images to the host while the trunk of the next sub-batch is still running.
 			    if (wholeBatch || !tailPerChunk) return;
-			    emitTail(plan, parity, out, gs, b0, nb);
+			    if (tailNb == 0) tailB0 = b0;
+			    tailNb += nb;
+			    if (tailNb < tailGroup && b0 + nb < B) return;
+			    emitTail(plan, parity, out, gs, tailB0, tailNb);
+			    tailNb = 0;
 			    tailsEmitted = true;
 		    });
 		if (tailsEmitted) {
@@ -828,15 +836,18 @@ __half *Engine::emitTrunk(std::vector<Op> &plan, TrunkState &ts, const std::stri
 	ta.lead_in = lead ? leadIn : nullptr;
 	// JU_TRUNK_SUBBATCH: a large batch runs as consecutive launches of this
 	// many streams, each through ALL layers, so that the three trunk tensors of one launch stay
-	// resident in L2 (2 PSP streams = 100 MB of the 126 MB; one launch over 16 streams would
-	// stream ~800 MB per layer through HBM).  Default (-1): as many streams as fit 85 % of the
-	// L2; 0 = one launch for the whole batch.
+	// resident in L2 (one launch over 16 PSP streams would stream ~800 MB per layer through HBM).
+	// Default (-1): as many streams as fit 45 % of the L2, i.e. ONE PSP stream (50 MB): with two
+	// (100 MB of the 126 MB) the reads still hit, but ~80 % of every layer's output is written back
+	// to DRAM (ncu: 1.32 GB per launch, profiles/r02_ncu_trunk_df_b2_of_16.json) and, the 16-stream
+	// step being power-capped, that costs 3 % (1594 vs 1644 fps, 1700 vs 1747 MHz).
+	// 0 = one launch for the whole batch.
 	const std::size_t perStream = static_cast<std::size_t>(H) * W * cstride;
 	int chunk = envInt("JU_TRUNK_SUBBATCH", -1);
 	if (chunk < 0) {
 		int l2 = 0;
 		cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, m_Device);
-		const double budget = 0.85 * static_cast<double>(l2);
+		const double budget = 0.45 * static_cast<double>(l2);
 		chunk = static_cast<int>(budget / (3.0 * perStream * sizeof(__half)));
 		if (chunk < 1) chunk = 1;
 	}
