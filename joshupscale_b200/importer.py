@@ -10,8 +10,7 @@ tool takes either
   * an `.npz` whose keys are Keras variable paths, e.g. written where TensorFlow
     is installed with
         np.savez("w.npz", **{v.path: v.numpy() for v in model.variables})
-  * a Keras 3 `.weights.h5` (needs `h5py`, which this image does not ship: the
-    reader is exercised only where h5py is importable),
+  * a Keras 3 `.weights.h5`, read by the numpy-only HDF5 reader in `hdf5_lite.py` (no h5py),
 
 recognises the flow / generator variables by their layer-relative path whatever
 model scopes precede them (`final/full/generator_1/...`, `:0` suffixes, Keras'
@@ -188,14 +187,8 @@ def read_keras_h5(path: str) -> Dict[str, np.ndarray]:
     back to a variable name from the layer's tensor ranks (conv: kernel[, bias]; batch norm:
     gamma, beta, moving_mean, moving_variance).  Legacy files that store named datasets
     (`.../kernel:0`) pass through unchanged."""
-    try:
-        import h5py  # noqa: PLC0415
-    except ImportError as exc:  # pragma: no cover - not installed in this image
-        raise ImportError_("reading .h5 needs the h5py package; convert to .npz where Keras is "
-                           "installed (see the module docstring)") from exc
-    flat: Dict[str, np.ndarray] = {}
-    with h5py.File(path, "r") as f:
-        f.visititems(lambda n, o: flat.__setitem__(n, np.asarray(o)) if isinstance(o, h5py.Dataset) else None)
+    from .hdf5_lite import read_datasets  # noqa: PLC0415
+    flat = {name.strip("/"): arr for name, arr in read_datasets(path, skip_unsupported=True).items()}
     return rename_indexed_vars(flat)
 
 

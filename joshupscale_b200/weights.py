@@ -212,8 +212,9 @@ def load_model(path: str) -> Tuple[ModelConfig, "OrderedDict[str, np.ndarray]"]:
     act_name = {v: k_ for k_, v in _ACT.items()}
     pad = 0
     if ph != fh or pw != fw:
-        # smallest factor that reproduces the padded size
-        for cand in range(2, 257):
+        # the container stores the padded size, not the factor: take the reference's factor (8) when
+        # it reproduces the padded size, else the smallest that does
+        for cand in (8, *range(2, 257)):
             if (fh + cand - 1) // cand * cand == ph and (fw + cand - 1) // cand * cand == pw:
                 pad = cand
                 break
