@@ -1,4 +1,8 @@
-"""Round-2 probe (GPU): CTA-pair (cta_group::2) persistent trunk vs the single-CTA trunk."""
+"""Round-2 probe (GPU): a trunk variant selected by environment switches vs the default trunk.
+
+    python bench_tools/probe_r2c.py                      # JU_TRUNK_PAIR=1 (CTA pairs), with and without cooperative launch
+    python bench_tools/probe_r2c.py JU_TRUNK_DIRECT=1    # any KEY=VALUE[,KEY=VALUE] sets, one run each
+"""
 
 import json
 import os
@@ -39,10 +43,13 @@ def run(preset, batch, env):
 
 
 def main():
+    sets = [dict(kv.split("=", 1) for kv in arg.split(",")) for arg in sys.argv[1:]]
+    if not sets:
+        sets = [{"JU_TRUNK_PAIR": "1"}, {"JU_TRUNK_PAIR": "1", "JU_TRUNK_COOP": "0"}]
     for preset, batch in (("small", 1), ("psp_fast", 1), ("psp_quality", 1), ("psp_quality", 2), ("psp_quality", 16)):
         base, g0, err = run(preset, batch, {})
         print(json.dumps({"preset": preset, "batch": batch, "env": {}, "groups": g0, "error": err}), flush=True)
-        for env in ({"JU_TRUNK_PAIR": "1"}, {"JU_TRUNK_PAIR": "1", "JU_TRUNK_COOP": "0"}):
+        for env in sets:
             out, g, err = run(preset, batch, env)
             same = None if out is None or base is None else bool(np.array_equal(out, base))
             print(json.dumps({"preset": preset, "batch": batch, "env": env, "groups": g, "bit_identical": same,
