@@ -560,6 +560,9 @@ void Engine::buildPlan(int parity, int variant) {
 		// the tail kernel wants >= 2 streams per launch (1020 tiles of one PSP stream are 6.9 waves on
 		// 148 SMs): finished trunk launches are collected until that many streams are waiting
 		const int tailGroup = std::max(1, envInt("JU_TAIL_GROUP", 2));
+		// ... but the LAST group's device-to-host copy has nothing left to hide behind, so the group
+		// boundaries are shifted to leave that many streams (default 1) for the final tail
+		const int tailLast = std::max(1, std::min(tailGroup, envInt("JU_TAIL_LAST", 1)));
 		int tailB0 = 0, tailNb = 0;
 		cur = emitTrunk(plan, m_GenTrunk, "generator", s.genBlocks, t0, t1, t2, gs, H, W, conv1InTrunk ? gc1 : nullptr,
 		    m_GenIn.as<__half>(), [&](const __half *out, int b0, int nb, bool wholeBatch) {
@@ -569,7 +572,9 @@ void Engine::buildPlan(int parity, int variant) {
 			    if (wholeBatch || !tailPerChunk) return;
 			    if (tailNb == 0) tailB0 = b0;
 			    tailNb += nb;
-			    if (tailNb < tailGroup && b0 + nb < B) return;
+			    const int remaining = B - (b0 + nb);
+			    const bool boundary = remaining >= tailLast && (remaining - tailLast) % tailGroup == 0;
+			    if (tailNb < tailGroup && remaining > 0 && !boundary) return;
 			    emitTail(plan, parity, out, gs, tailB0, tailNb);
 			    tailNb = 0;
 			    tailsEmitted = true;
