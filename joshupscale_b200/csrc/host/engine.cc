@@ -1,10 +1,12 @@
 #include "engine.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
 
 namespace ju {
 
@@ -71,7 +73,20 @@ Engine::Engine(const ModelFile &model, int device, int batch)
 	// against other processes); measured free: 171.8 vs 171.9 us for the psp_fast trunk
 	m_TrunkCooperative = envInt("JU_TRUNK_COOP", 1) != 0;
 	m_WaitTimeoutMs = envInt("JU_WAIT_TIMEOUT_MS", 0);
-	m_CopyThreads = envInt("JU_COPY_THREADS", 4);  // 0 = let the driver stage pageable images
+	// Copy pool for pageable caller images: 0 = let the driver stage them.  Default: up to 4 threads,
+	// but no more than this process' share of the host cores when there is one process per GPU
+	// (8 ranks x 4 spinning threads on a 16-core host collapsed to half the pinned throughput).
+	{
+		int devices = 1;
+		if (cudaGetDeviceCount(&devices) != cudaSuccess || devices < 1) devices = 1;
+		const int cores = static_cast<int>(std::max(1u, std::thread::hardware_concurrency()));
+		const int share = std::max(1, cores / devices);
+		m_CopyThreads = envInt("JU_COPY_THREADS", std::min(4, share));
+	}
+	// how long the calling thread polls for the next output band before it parks the pool and blocks
+	// on the event: a batch-1 frame (0.4 - 0.7 ms) is polled through, a many-stream frame (10 ms)
+	// leaves the cores to other processes between its tail groups
+	m_CopySpinUs = envInt("JU_COPY_SPIN_US", m_Batch == 1 ? 2000 : 100);
 	JU_CUDA(cudaStreamCreateWithFlags(&m_Stream, cudaStreamNonBlocking));
 	JU_CUDA(cudaStreamCreateWithFlags(&m_CopyStream, cudaStreamNonBlocking));
 	try {
@@ -1283,7 +1298,7 @@ void Engine::process(int n, const ju_image *inputs, const ju_image *outputs) {
 				const std::size_t used = m_BandEventsUsed++;
 				if (used == m_BandEvents.size()) {
 					cudaEvent_t ev = nullptr;
-					JU_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+					JU_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming | cudaEventBlockingSync));
 					m_BandEvents.push_back(ev);
 				}
 				JU_CUDA(cudaEventRecord(m_BandEvents[used], m_CopyStream));
@@ -1305,11 +1320,19 @@ void Engine::process(int n, const ju_image *inputs, const ju_image *outputs) {
 			cudaEvent_t ready = nullptr;
 			for (const BandCopy &band : m_BandCopies) {
 				if (band.event != ready) {
+					const auto t0 = std::chrono::steady_clock::now();
 					for (;;) {
 						const cudaError_t q = cudaEventQuery(band.event);
 						if (q == cudaSuccess) break;
 						if (q != cudaErrorNotReady) checkCuda(q, "cudaEventQuery");
-						m_Pool->help();
+						if (m_Pool->help()) continue;
+						if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(m_CopySpinUs)) {
+							// nothing to copy and the band is far away: park the workers and sleep on the event
+							m_Pool->end();
+							JU_CUDA(cudaEventSynchronize(band.event));
+							m_Pool->begin();
+							break;
+						}
 					}
 					ready = band.event;
 				}

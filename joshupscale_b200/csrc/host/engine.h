@@ -155,6 +155,7 @@ private:
 		cudaEvent_t event;  // the band has arrived in pinned memory
 	};
 	int m_CopyThreads = 4;
+	int m_CopySpinUs = 100;
 	std::unique_ptr<HostCopyPool> m_Pool;
 	PinnedBuffer m_InPinned, m_OutPinned;
 	std::vector<BandCopy> m_BandCopies;     // this frame's bands, in copy-stream order
