@@ -105,6 +105,109 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int iters, long long *cycl
 	}
 }
 
+
+// The exact issue pattern of trunk_ts_tc.cu: halo pitch 66 pixels, SBO 1024, three accumulator stages of 64
+// columns, weights from column WCOL, optionally the output-lane masks on half of the MMAs
+__device__ __forceinline__ void umma_ts_f16_masked(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc,
+    uint32_t m01, uint32_t m23) {
+	asm volatile(
+	    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+	    "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %6, %6}, p;\n\t}" ::"r"(d_tmem),
+	    "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc), "r"(m01), "r"(m23)
+	    : "memory");
+}
+
+template <int PITCH, int WCOL, bool MASKED, int NACC, int COMMIT = 0>
+__global__ void __launch_bounds__(128, 1) ts_pattern_kernel(int iters, long long *cycles) {
+	extern __shared__ __align__(1024) unsigned char smem_raw[];
+	__shared__ uint32_t tmem_slot;
+	__shared__ __align__(8) unsigned long long bar;
+	__shared__ __align__(8) unsigned long long bar2[2];
+	const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+	const int warp = threadIdx.x / 32;
+	if (warp == 0) {
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512));
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+	}
+	if (threadIdx.x == 0) {
+		mbar_init(smem_u32(&bar), 1);
+		mbar_init(smem_u32(&bar2[0]), 1);
+		mbar_init(smem_u32(&bar2[1]), 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	fill_smem(smem_raw, 1024 + 3 * 4 * PITCH * 128);
+	tcgen05_fence_before();
+	__syncthreads();
+	tcgen05_fence_after();
+	const uint32_t tmem = tmem_slot;
+	const uint32_t idesc = make_idesc(64);
+	if (warp == 0) {
+		long long t0 = clock64();
+		for (int it = 0; it < iters; ++it) {
+			const uint32_t d = tmem + (it % NACC) * 64;
+			const uint32_t x_base = base + (it % 3) * 4 * PITCH * 128;
+#pragma unroll
+			for (int st = 0; st < 12; ++st) {
+				const int kx = st >> 2, q4 = st & 3;
+				const int r = q4 == 0 ? 1 : (q4 == 1 ? 2 : (q4 == 2 ? 0 : 3));
+				const int g = kx * 3 + (q4 < 2 ? q4 + 1 : 0);
+#pragma unroll
+				for (int j = 0; j < 4; ++j) {
+					if (elect_one_sync()) {
+						const uint64_t bd = make_smem_desc(x_base + (r * PITCH + kx) * 128 + j * 32, 1024u, 0);
+						const uint32_t a = tmem + WCOL + (g * 4 + j) * 8;
+						const uint32_t acc = (st | j) != 0;
+						if (MASKED && r == 0) umma_ts_f16_masked(d, a, bd, idesc, acc, 0u, 0xffffffffu);
+						else if (MASKED && r == 3) umma_ts_f16_masked(d, a, bd, idesc, acc, 0xffffffffu, 0u);
+						else umma_ts_f16(d, a, bd, idesc, acc);
+					}
+					__syncwarp();
+				}
+			}
+			if (COMMIT >= 1) {
+				if (elect_one_sync()) {
+					umma_commit(smem_u32(&bar2[0]));
+					if (COMMIT >= 2) umma_commit(smem_u32(&bar2[1]));
+				}
+				__syncwarp();
+			}
+		}
+		if (elect_one_sync()) umma_commit(smem_u32(&bar));
+		__syncwarp();
+		spin(smem_u32(&bar), 0);
+		long long t1 = clock64();
+		if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+	}
+	tcgen05_fence_before();
+	__syncthreads();
+	if (warp == 0) {
+		tcgen05_fence_after();
+		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+	}
+}
+
+template <int PITCH, int WCOL, bool MASKED, int NACC, int COMMIT = 0>
+void run_pattern(const char *what) {
+	const int iters = 2000;
+	long long *d;
+	cudaMalloc(&d, 148 * sizeof(long long));
+	cudaMemset(d, 0, 148 * sizeof(long long));
+	const int smem = 2048 + 3 * 4 * PITCH * 128;
+	fprintf(stderr, "pattern %s: smem %d\n", what, smem);
+	cudaFuncSetAttribute(ts_pattern_kernel<PITCH, WCOL, MASKED, NACC, COMMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+	ts_pattern_kernel<PITCH, WCOL, MASKED, NACC, COMMIT><<<148, 128, smem>>>(iters, d);
+	ts_pattern_kernel<PITCH, WCOL, MASKED, NACC, COMMIT><<<148, 128, smem>>>(iters, d);
+	cudaError_t e = cudaDeviceSynchronize();
+	fprintf(stderr, "sync: %s\n", cudaGetErrorString(e));
+	long long h[148];
+	cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+	double s = 0;
+	for (int i = 0; i < 148; ++i) s += h[i];
+	printf("trunk_ts pattern (%s): %.1f cycles per MMA, %.0f per unit %s\n", what, s / 148 / (iters * 48.0), s / 148 / iters,
+	    e == cudaSuccess ? "" : cudaGetErrorString(e));
+	cudaFree(d);
+}
+
 template <int N, bool TS>
 void run() {
 	const int iters = 2000;
@@ -137,6 +240,13 @@ void run() {
 }
 
 int main() {
+	setvbuf(stdout, nullptr, _IONBF, 0);
+	run_pattern<66, 192, true, 3>("pitch 66, weights at col 192, masks, 3 acc");
+	run_pattern<66, 192, false, 3>("pitch 66, col 192, no masks, 3 acc");
+	run_pattern<66, 192, false, 3, 1>("same + 1 commit per unit");
+	run_pattern<66, 192, false, 3, 2>("same + 2 commits per unit");
+	run_pattern<66, 224, false, 2>("pitch 66, col 224, no masks, 2 acc");
+	run_pattern<64, 192, true, 3>("pitch 64, col 192, masks, 3 acc");
 	run<64, true>();
 	run<128, true>();
 	run<256, true>();

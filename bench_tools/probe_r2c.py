@@ -52,8 +52,9 @@ def main():
         for env in sets:
             out, g, err = run(preset, batch, env)
             same = None if out is None or base is None else bool(np.array_equal(out, base))
+            diff = None if out is None or base is None else int(np.abs(out.astype(np.int32) - base.astype(np.int32)).max())
             print(json.dumps({"preset": preset, "batch": batch, "env": env, "groups": g, "bit_identical": same,
-                              "error": err}), flush=True)
+                              "max_abs_diff_u8": diff, "error": err}), flush=True)
 
 
 if __name__ == "__main__":

@@ -35,6 +35,15 @@ __device__ __forceinline__ void umma_ts_f16(uint32_t d_tmem, uint32_t a_tmem, ui
 	    "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
 	    : "memory");
 }
+// same, with a lane mask: bit i of word w set = lane 32 * w + i of D is NOT written
+__device__ __forceinline__ void umma_ts_f16_masked(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc,
+    uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
+	asm volatile(
+	    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+	    "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}" ::"r"(d_tmem),
+	    "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc), "r"(m0), "r"(m1), "r"(m2), "r"(m3)
+	    : "memory");
+}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
 	asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
 	    "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
@@ -115,17 +124,18 @@ unit_kernel(const __half *x, const __half *w, const float *bias, const __half *r
 	}
 
 	// ---- weights into tensor memory: thread m owns row m of every stacked slice ------------
+	// 9 stored groups: (kx, t = 0) = [W(0, kx); W(2, kx)] serves input row 0 (upper half only) AND input row 3
+	// (lower half only) through the output-lane mask; (kx, t = 1, 2) = [W(t, kx); W(t - 1, kx)] serve input rows 1, 2
 	{
 		const int m = threadIdx.x, h = m / 64, c = m % 64;
-		for (int g = 0; g < 12; ++g) {
-			const int r = g / 3, kx = g % 3, ky = r - h;
+		for (int g = 0; g < 9; ++g) {
+			const int kx = g / 3, t = g % 3;
+			const int ky = t == 0 ? (h ? 2 : 0) : t - h;
 			for (int j = 0; j < 4; ++j) {
-				uint32_t v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-				if (ky >= 0 && ky <= 2) {
-					const uint4 *src = reinterpret_cast<const uint4 *>(w + ((ky * 3 + kx) * 64 + c) * 64 + j * 16);
-					const uint4 a = src[0], b = src[1];
-					v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-				}
+				uint32_t v[8];
+				const uint4 *src = reinterpret_cast<const uint4 *>(w + ((ky * 3 + kx) * 64 + c) * 64 + j * 16);
+				const uint4 a = src[0], b = src[1];
+				v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 				tmem_st8(tmem + lane_base + kWCol + (g * 4 + j) * 8, v);
 			}
 		}
@@ -139,11 +149,20 @@ unit_kernel(const __half *x, const __half *w, const float *bias, const __half *r
 	if (warp == 0) {
 		const uint32_t idesc = make_idesc(kN);
 		if (elect_one_sync()) {
-			for (int g = 0; g < 12; ++g) {
-				const int r = g / 3, kx = g % 3;
-				for (int j = 0; j < 4; ++j) {
-					const uint64_t bd = make_smem_desc(base + halo + (r * kPitch + kx) * 128 + j * 32, 1024u, 0);
-					umma_ts_f16(tmem + kAccCol, tmem + kWCol + (g * 4 + j) * 8, bd, idesc, (g | j) != 0);
+			bool first = true;
+			for (int kx = 0; kx < 3; ++kx) {
+				for (int ri = 0; ri < 4; ++ri) {
+					// an unmasked group goes first: the masked ones must not be the ones that initialise D
+					const int r = ri == 0 ? 1 : (ri == 1 ? 2 : (ri == 2 ? 0 : 3));
+					const int g = kx * 3 + (r == 0 || r == 3 ? 0 : r);
+					for (int j = 0; j < 4; ++j) {
+						const uint64_t bd = make_smem_desc(base + halo + (r * kPitch + kx) * 128 + j * 32, 1024u, 0);
+						const uint32_t a = tmem + kWCol + (g * 4 + j) * 8;
+						if (r == 0) umma_ts_f16_masked(tmem + kAccCol, a, bd, idesc, !first, 0u, 0u, 0xffffffffu, 0xffffffffu);
+						else if (r == 3) umma_ts_f16_masked(tmem + kAccCol, a, bd, idesc, !first, 0xffffffffu, 0xffffffffu, 0u, 0u);
+						else umma_ts_f16(tmem + kAccCol, a, bd, idesc, !first);
+						first = false;
+					}
 				}
 			}
 			umma_commit(smem_u32(&bar));
