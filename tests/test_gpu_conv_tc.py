@@ -234,6 +234,11 @@ def test_dataflow_trunk_race_stress(tmp_path):
     {"JU_COPY_THREADS": "0"},
     {"JU_TRUNK_PAIR": "1"},
     {"JU_TRUNK_PAIR": "1", "JU_TRUNK_COOP": "0", "JU_TRUNK_SUBBATCH": "1"},
+    {"JU_COPY_SPIN_US": "0"},                              # copy pool parks and blocks on every band event
+    {"JU_COPY_THREADS": "1", "JU_COPY_SPIN_US": "0"},      # the calling thread alone
+    {"JU_TRUNK_SUBBATCH": "1", "JU_TAIL_LAST": "2"},       # tail groups (0), (1, 2)
+    {"JU_TRUNK_SUBBATCH": "1", "JU_TAIL_GROUP": "1"},      # one tail per stream
+    {"JU_TRUNK_SUBBATCH": "1", "JU_TAIL_GROUP": "3", "JU_TAIL_LAST": "3"},
 ])
 def test_execution_switches_do_not_change_the_bytes(tmp_path, env):
     """Scheduling / fusion switches only change HOW the frame is executed:
