@@ -1,5 +1,6 @@
 // Fused generator tail on tcgen05: conv_trans_1 (+BN+act) as a 1x1 GEMM to
-// 4 x 32 channels, and - entirely inside its epilogue - conv_trans_2 + bias +
+// 4 x 32 channels, and - entirely inside its epilogue - conv_trans_2 (a second,
+// tiny GEMM whose A operand the epilogue threads write into tensor memory) + bias +
 // tanh + legacy-bilinear x4 of the input frame + add + clip + uint8 BGRX pack +
 // fp16 recurrent-state write.  The [2H,2W,32] intermediate never exists in
 // memory: 16 epilogue warps, each thread owns one mid-resolution pixel (one of
@@ -42,9 +43,9 @@ struct TailParams {
 	int act;
 	float slope;
 	int pdl;
-	// conv_trans_2 (s = i2*2+j2, o, c; fp16-representable values), its bias and the folded BN bias of
-	// conv_trans_1 (the same 32 values for each of its 4 sub-pixels) travel IN the kernel parameters:
-	// the unrolled epilogue reads them as constant-bank operands instead of 96 LDS.128 per thread
+	// conv_trans_2 (s = i2*2+j2, o, c; fp16-representable values: every CTA turns them into the 2 KB
+	// B tile of the second GEMM), its bias and the folded BN bias of conv_trans_1 (the same 32 values
+	// for each of its 4 sub-pixels) travel IN the kernel parameters: constant-bank operands
 	float w2[4 * 3 * 32];
 	float bias2[4];
 	float bias1[32];
@@ -62,19 +63,38 @@ __device__ __forceinline__ float tanh_fast(float x) {
 	return 1.f - __fdividef(2.f, e + 1.f);
 }
 
-// packed fp32x2 FMA (sm_100): acc.{lo,hi} += a.{lo,hi} * b.{lo,hi}
-__device__ __forceinline__ void ffma2(unsigned long long &acc, unsigned long long a, unsigned long long b) {
-	asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+// conv_trans_2 on the tensor core: the activation of conv_trans_1 is rounded to fp16 anyway (the
+// engine's storage contract) and w2 holds fp16-representable values, so z = m * w2^T is one tiny
+// TS-form GEMM per sub-pixel group: every thread writes its pixel's 32 channels as one row of the A
+// operand into tensor memory (tcgen05.st, lane = its own TMEM lane), one elected thread of the
+// group's four warps issues two M128 N16 K16 MMAs against the 2 KB w2 tile in shared memory, and
+// every thread reads its 12 sums back with tcgen05.ld.  This replaces 192 packed fp32 FMAs and as
+// many constant loads per pixel in a kernel that is bound by instruction issue.
+constexpr uint32_t kA2Col = 256u;  // 4 groups x 16 columns: [128 lanes x 32 ch fp16]
+constexpr uint32_t kD2Col = 320u;  // 4 groups x 16 columns: [128 lanes x 16 fp32] (12 used)
+constexpr uint32_t kW2Tile = 16u * 128u;
+
+__device__ __forceinline__ void umma_ts_f16(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+	asm volatile(
+	    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+	    "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+	    "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+	    : "memory");
 }
-__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
-	unsigned long long r;
-	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-	return r;
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+	asm volatile(
+	    "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+	    "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+	    "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+	    : "memory");
 }
-__device__ __forceinline__ float sum2(unsigned long long v) {
-	float lo, hi;
-	asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-	return lo + hi;
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+	asm volatile(
+	    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+	    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+	      "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+	    : "r"(taddr)
+	    : "memory");
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -91,10 +111,12 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 	auto tempty_bar = [&](int s) { return bar_base + 8u * (18 + s); };
 	const uint32_t w_bar = bar_base + 8u * 20;
 	const uint32_t tmem_slot = bar_base + 8u * 21;
+	auto d2_bar = [&](int g) { return bar_base + 8u * (24 + g); };
+	const uint32_t w2_base = bar_base + 1024u;  // SWIZZLE_128B tile: 16 rows (s2 * 3 + o) x 64 ch fp16, zero padded
 
 	const int warp = threadIdx.x >> 5;
 	const int lane = threadIdx.x & 31;
-	constexpr uint32_t kTmemCols = 256;  // 2 accumulator stages x 128 columns
+	constexpr uint32_t kTmemCols = 512;  // 2 accumulator stages x 128 columns, conv_trans_2 operand and result
 
 	if (warp == 0 && lane == 0) {
 		for (int s = 0; s < kStages; ++s) {
@@ -106,8 +128,16 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 			mbar_init(tempty_bar(s), kEpiWarps);
 		}
 		mbar_init(w_bar, 1);
+		for (int g = 0; g < 4; ++g) mbar_init(d2_bar(g), 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
+	for (int idx = threadIdx.x; idx < 16 * 64; idx += kThreads) {
+		const uint32_t n = static_cast<uint32_t>(idx) >> 6, c = static_cast<uint32_t>(idx) & 63u;
+		const float v = (n < 12u && c < 32u) ? p.w2[n * 32u + c] : 0.f;
+		*reinterpret_cast<__half *>(smem_gen + (w2_base - smem_base) + n * 128u + ((((c >> 3) ^ (n & 7u)) << 4) | ((c & 7u) << 1))) =
+		    __float2half_rn(v);
+	}
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 	if (warp == 1) {
 		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
 		             "r"(kTmemCols)
@@ -227,49 +257,55 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 			__syncwarp();
 			W.sync_warp();
 			if (lane == 0 && !W.dead) mbar_arrive(tempty_bar(as));
-			float m[32];
+			uint32_t mh[16];
 #pragma unroll
-			for (int c4 = 0; c4 < 8; ++c4) {
-				const float bb[4] = {p.bias1[c4 * 4], p.bias1[c4 * 4 + 1], p.bias1[c4 * 4 + 2], p.bias1[c4 * 4 + 3]};
-#pragma unroll
-				for (int e = 0; e < 4; ++e) {
-					float v = __uint_as_float(acc[c4 * 4 + e]) + bb[e];
-					if (p.act == ACT_RELU) {
-						v = fmaxf(v, 0.f);
-					} else if (p.act == ACT_LRELU) {
-						v = v >= 0.f ? v : v * p.slope;
-					}
-					// the engine's storage contract rounds this activation to fp16
-					m[c4 * 4 + e] = __half2float(__float2half_rn(v));
+			for (int c2 = 0; c2 < 16; ++c2) {
+				float v0 = __uint_as_float(acc[2 * c2]) + p.bias1[2 * c2];
+				float v1 = __uint_as_float(acc[2 * c2 + 1]) + p.bias1[2 * c2 + 1];
+				if (p.act == ACT_RELU) {
+					v0 = fmaxf(v0, 0.f);
+					v1 = fmaxf(v1, 0.f);
+				} else if (p.act == ACT_LRELU) {
+					v0 = v0 >= 0.f ? v0 : v0 * p.slope;
+					v1 = v1 >= 0.f ? v1 : v1 * p.slope;
 				}
+				// the engine's storage contract rounds this activation to fp16
+				const __half2 hh = __floats2half2_rn(v0, v1);
+				mh[c2] = *reinterpret_cast<const uint32_t *>(&hh);
 			}
-			// conv_trans_2: z[s][o] = sum_c m[c] * w2[s][o][c], s = i2*2+j2; packed fp32x2
-			// FMAs accumulate even / odd channels separately (fp32 throughout)
-			unsigned long long mp[16];
+			// conv_trans_2: z[s][o] = sum_c m[c] * w2[s][o][c] as D2[128 pixels x 16] = A2[128 x 32] * w2^T
+			tmem_st16(tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + kA2Col + static_cast<uint32_t>(q * 16), mh);
+			asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+			tcgen05_fence_before();
+			asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");  // the four warps of this sub-pixel group
+			if (q4 == 0) {
+				tcgen05_fence_after();
+				if (elect_one_sync() && !W.dead) {
+					const uint32_t hi2 = static_cast<uint32_t>(make_smem_desc(0, 1024u, 0) >> 32);
+					const uint32_t lo2 = (1u << 16) | (w2_base >> 4);
+					const uint32_t idesc2 = make_idesc(16);
 #pragma unroll
-			for (int c2 = 0; c2 < 16; ++c2) mp[c2] = pack2(m[2 * c2], m[2 * c2 + 1]);
-			unsigned long long zp[4][3];
-#pragma unroll
-			for (int s2 = 0; s2 < 4; ++s2)
-#pragma unroll
-				for (int o = 0; o < 3; ++o) zp[s2][o] = 0ull;
-#pragma unroll
-			for (int c4 = 0; c4 < 8; ++c4) {
-#pragma unroll
-				for (int s2 = 0; s2 < 4; ++s2) {
-#pragma unroll
-					for (int o = 0; o < 3; ++o) {
-						const float *wq = p.w2 + (s2 * 3 + o) * 32 + c4 * 4;
-						ffma2(zp[s2][o], mp[c4 * 2 + 0], pack2(wq[0], wq[1]));
-						ffma2(zp[s2][o], mp[c4 * 2 + 1], pack2(wq[2], wq[3]));
+					for (int k16 = 0; k16 < 2; ++k16) {
+						umma_ts_f16(tmem_base + kD2Col + static_cast<uint32_t>(q * 16),
+						    tmem_base + kA2Col + static_cast<uint32_t>(q * 16 + k16 * 8),
+						    (static_cast<uint64_t>(hi2) << 32) | (lo2 + k16 * 2u), idesc2, k16 != 0 ? 1u : 0u);
 					}
+					umma_commit(d2_bar(q));
 				}
+				__syncwarp();
 			}
+			W.wait(d2_bar(q), static_cast<uint32_t>(it & 1), 6);
+			tcgen05_fence_after();
+			uint32_t zr[16];
+			__syncwarp();
+			tmem_ld16(tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + kD2Col + static_cast<uint32_t>(q * 16), zr);
+			tmem_ld_wait();
+			tcgen05_fence_before();
 			float z[4][3];
 #pragma unroll
 			for (int s2 = 0; s2 < 4; ++s2)
 #pragma unroll
-				for (int o = 0; o < 3; ++o) z[s2][o] = sum2(zp[s2][o]);
+				for (int o = 0; o < 3; ++o) z[s2][o] = __uint_as_float(zr[s2 * 3 + o]);
 			if (valid) {
 #pragma unroll
 				for (int i2 = 0; i2 < 2; ++i2) {
@@ -336,7 +372,7 @@ EncodeTiledFn encodeTiled() {
 	return fn;
 }
 
-constexpr uint32_t kSmemBytes = 1024u + kStages * kATile + kBBytes + 256u;
+constexpr uint32_t kSmemBytes = 1024u + kStages * kATile + kBBytes + 1024u + kW2Tile;
 
 }  // namespace
 
