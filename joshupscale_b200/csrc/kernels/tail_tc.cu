@@ -230,7 +230,7 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 			const int y = y0 + (row >> 3), x = x0 + (row & 7);
 			const bool valid = y < p.h && x < p.w;
 			// bilinear corners of the LR frame (src = dst/4, clamp at the far edge)
-			float cr[4][3];
+			float cr[4][3] = {};
 			const FrameIO f = p.io[b];
 			const float bright = p.brightness ? p.brightness[b] : 0.f;
 			if (valid) {
@@ -294,6 +294,23 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 				}
 				__syncwarp();
 			}
+			// while the second GEMM is in flight: the bilinear x4 of the input frame for this thread's
+			// 2x2 HR pixels (independent of z; same operation order as the reference)
+			float up[4][3];
+#pragma unroll
+			for (int i2 = 0; i2 < 2; ++i2) {
+				const float ty = static_cast<float>(2 * i + i2) * 0.25f;
+#pragma unroll
+				for (int j2 = 0; j2 < 2; ++j2) {
+					const float tx = static_cast<float>(2 * j + j2) * 0.25f;
+#pragma unroll
+					for (int o = 0; o < 3; ++o) {
+						const float topv = __fadd_rn(cr[0][o], __fmul_rn(__fsub_rn(cr[1][o], cr[0][o]), tx));
+						const float botv = __fadd_rn(cr[2][o], __fmul_rn(__fsub_rn(cr[3][o], cr[2][o]), tx));
+						up[i2 * 2 + j2][o] = __fadd_rn(topv, __fmul_rn(__fsub_rn(botv, topv), ty));
+					}
+				}
+			}
 			W.wait(d2_bar(q), static_cast<uint32_t>(it & 1), 6);
 			tcgen05_fence_after();
 			uint32_t zr[16];
@@ -310,21 +327,16 @@ tail_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
 				for (int i2 = 0; i2 < 2; ++i2) {
 					const int R = 2 * i + i2;  // HR row inside the LR pixel's 4x4 block
-					const float ty = static_cast<float>(R) * 0.25f;
 					const int Y = 4 * y + R;
 					uchar4 px[2];
 					__align__(16) __half st[2][4];
 #pragma unroll
 					for (int j2 = 0; j2 < 2; ++j2) {
-						const float tx = static_cast<float>(2 * j + j2) * 0.25f;
 						unsigned char o8[3];
 #pragma unroll
 						for (int o = 0; o < 3; ++o) {
 							const float zz = tanh_fast(z[i2 * 2 + j2][o] + b2[o]);
-							const float topv = __fadd_rn(cr[0][o], __fmul_rn(__fsub_rn(cr[1][o], cr[0][o]), tx));
-							const float botv = __fadd_rn(cr[2][o], __fmul_rn(__fsub_rn(cr[3][o], cr[2][o]), tx));
-							const float up = __fadd_rn(topv, __fmul_rn(__fsub_rn(botv, topv), ty));
-							const float r = fminf(fmaxf(__fadd_rn(up, zz), -0.5f), 0.5f);
+							const float r = fminf(fmaxf(__fadd_rn(up[i2 * 2 + j2][o], zz), -0.5f), 0.5f);
 							o8[o] = static_cast<unsigned char>(static_cast<int>(__fmul_rn(__fadd_rn(r, 0.5f), 255.0f)));
 							st[j2][o] = __float2half_rn(r - bright);
 							if (p.out_raw) {
